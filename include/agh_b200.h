@@ -1,0 +1,170 @@
+/*
+ * agh_b200.h -- C ABI of the B200-native AGH rollout library (libagh_b200.so).
+ *
+ * The reference (RoyalSkye/AGH, Construction_based/, "CB/") has no FFI layer: its hot path is
+ * Python calling PyTorch ATen.  This header is the boundary a maintainer binds with ctypes
+ * (INTEGRATION.md shows the stub): plain device pointers, sizes and a CUDA stream handle; no
+ * torch types; every function returns 0 on success or a negative AGH_E* code, never throws, and
+ * owns no memory (the caller allocates every output, e.g. with torch.empty).  All entry points
+ * are asynchronous on `stream` and re-entrant per stream; there is no global state besides the
+ * last-error string.
+ *
+ * Shapes: B instances, N flights, n = N+1 nodes (node 0 = depot), D = 128, H = 8 heads of 16,
+ * FF = 512, 3 encoder layers, 92 airport locations (91 gates + depot).
+ *
+ * Each function cites the reference code it replaces (file:line under CB/).
+ */
+#ifndef AGH_B200_H
+#define AGH_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGH_D 128
+#define AGH_H 8
+#define AGH_FF 512
+#define AGH_LAYERS 3
+#define AGH_NODE_SIZE 92
+#define AGH_KEY_STRIDE 132 /* floats per node row of the staged K'/V/LK' matrices (528 B, bank-conflict-free) */
+#define AGH_MAX_N 320
+
+enum {
+  AGH_OK = 0,
+  AGH_E_ARG = -1,      /* bad argument (null pointer, size out of range) */
+  AGH_E_CUDA = -2,     /* CUDA runtime error; see agh_last_error() */
+  AGH_E_UNSUPPORTED = -3
+};
+
+/* decode modes (attention_model.py:372-390) */
+enum { AGH_GREEDY = 0, AGH_SAMPLING = 1, AGH_REPLAY = 2 };
+
+/* bits of the per-instance status word written by agh_get_costs (problem_agh.py:24-27,44,64) */
+enum { AGH_TOUR_INVALID = 1, AGH_CAPACITY_EXCEEDED = 2, AGH_TW_VIOLATED = 4 };
+
+const char* agh_last_error(void);
+int agh_version(void);
+
+/* ---- packed weights -------------------------------------------------------------------------
+ * One f32 blob built by the host from the reference state_dict (agh_b200/nets/weights.py);
+ * order and sizes are fixed by the architecture, agh_wblob_floats() returns the total.
+ *   loc_emb[92][128] | init_w[3][128] | init_b[128] |
+ *   3 x { wqkv[128][384] | wo[128][128] | bn1_scale[128] | bn1_shift[128] | w1t[128][512] | b1[512] |
+ *         w2t[512][128] | b2[128] | bn2_scale[128] | bn2_shift[128] } |
+ *   wdec[128][512] (K'/4 | V | LK'=W_out^T W_lk/sqrt(128) | P_sc) | wfc_t[128][128] |
+ *   fleet_emb[10][128] | w_cap[128] | w_time[128]
+ */
+size_t agh_wblob_floats(void);
+
+/* ---- a1: fleet-batch assembly (train.py:40-57 == train.py:167-184 == eval.py:97-113) --------
+ * From the raw instance arrays and the per-level tw_left table build the node vectors of fleet f.
+ *   loc[B][N] i64 (1..91), type[B][N] i64 (0..2), departure[B][N] f32, demand_all[B][10][N] f32,
+ *   tw_left_levels[6][B][N] f32, duration3[3] f64 (fleet_info['duration'][f]),
+ *   next_duration3[3] f64 (fleet_info['next_duration'][precedence[f]]), nd_is_f32: level-4 quirk.
+ * Outputs: coord[B][n] u8, demand[B][N] f32, tw_left[B][n] f32, tw_right[B][n] f64, duration[B][n] f64.
+ */
+int agh_fleet_task(const int64_t* loc, const int64_t* type, const float* departure, const float* demand_all,
+                   const float* tw_left_levels, int level, int fleet /*1..10*/, const double* duration3,
+                   const double* next_duration3, int nd_is_f32, int B, int N, uint8_t* coord, float* demand,
+                   float* tw_left, double* tw_right, double* duration, void* stream);
+
+/* train.py:67  bat_tw_left[level+1] = max(bat_tw_left[level+1], serve_time[:,1:]) */
+int agh_chain_tw_left(float* tw_left_levels, int level, const float* serve /*[B][n]*/, int B, int N, void* stream);
+
+/* ---- a2+a3: init embedding + 3-layer graph attention encoder, eval-mode BatchNorm ------------
+ * (attention_model.py:272-294, graph_encoder.py:56-111,135-172,195-207)
+ *   h_out[B][n][128] f32.  workspace: agh_encoder_workspace_bytes(B,N) bytes.
+ */
+size_t agh_encoder_workspace_bytes(int B, int N);
+int agh_encode(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
+               const double* tw_right, int B, int N, float* h_out, void* workspace, void* stream);
+
+/* init embedding only (attention_model.py:272-294): h0[B][n][128] */
+int agh_init_embed(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
+                   const double* tw_right, int B, int N, float* h0, void* stream);
+
+/* ---- a4: decoder precompute (attention_model.py:392-414,604-611) ---------------------------
+ *   h[B][n][128] -> keys[B][3][n][132] (K'/4, V, LK'), psc[B][n][128], qbase[B][128]
+ *   fleet_ids[B] i32 (0..9) or NULL with `fleet` used for every instance.
+ */
+int agh_precompute(const float* wblob, const float* h, const int32_t* fleet_ids, int fleet, int B, int N,
+                   float* keys, float* psc, float* qbase, void* stream);
+
+/* ---- a5-a12, a14: fused persistent decode (attention_model.py:298-356,429-451,510-522,550-584;
+ *      state_agh.py:60-174), one CTA per instance for all T steps ----------------------------- */
+typedef struct {
+  /* inputs */
+  const float* keys;       /* [B][3][n][132] */
+  const float* psc;        /* [B][n][128] */
+  const float* qbase;      /* [B][128] */
+  const uint8_t* coord;    /* [B][n] */
+  const float* demand;     /* [B][N] */
+  const float* tw_left;    /* [B][n] */
+  const double* tw_right;  /* [B][n] */
+  const double* duration;  /* [B][n], duration[b][0] = 0 */
+  const float* distance;   /* [92*92] */
+  const float* wblob;      /* for w_cap / w_time */
+  /* shared-key replication (sample_many, utils/functions.py:171-188): instance r of B uses the
+     keys/psc/qbase/node vectors of instance r % key_mod when key_mod > 0 */
+  int key_mod;
+  int mode;                /* AGH_GREEDY | AGH_SAMPLING | AGH_REPLAY */
+  float temp;              /* softmax temperature (attention_model.py:447) */
+  uint64_t seed;           /* Philox key; counter = (instance id, step, node) */
+  int64_t id_offset;       /* global id of instance 0 (sharding-independent sampling) */
+  const int16_t* actions;  /* REPLAY: [B][t_stride] */
+  int replay_steps;        /* REPLAY: steps to run for every instance */
+  const float* inject_logp;/* optional [B][t_stride][n]: select from these log-probs instead */
+  int t_stride;            /* row stride (steps) of pi/actions/logp_sel/dumps; >= 2N-1 */
+  /* outputs */
+  int16_t* pi;             /* [B][t_stride], zero padded */
+  int32_t* steps;          /* [B] steps until the instance finished */
+  float* ll;               /* [B] sum of selected log-probs */
+  float* cost;             /* [B] closed-tour length */
+  float* serve;            /* [B][n] */
+  float* logp_sel;         /* optional [B][t_stride] */
+  float* logp_full;        /* optional [B][t_stride][n] */
+  uint32_t* mask_dump;     /* optional [B][t_stride][ceil(n/32)], bit=1 infeasible */
+  float* used_dump;        /* optional [B][t_stride] used capacity before the step */
+  double* cft_dump;        /* optional [B][t_stride] cur_free_time before the step */
+  int B, N;
+} agh_decode_args;
+
+int agh_decode(const agh_decode_args* args, void* stream);
+
+/* ---- a13: tour validation + cost (problem_agh.py:18-66) ------------------------------------
+ *   pi[B][T] i64.  cost[B] f32, status[B] i32 (0 = valid; AGH_TOUR_INVALID | ... otherwise).
+ */
+int agh_get_costs(const int64_t* pi, int T, const uint8_t* coord, const float* demand, const float* tw_left,
+                  const double* tw_right, const double* duration, const float* distance, int B, int N,
+                  float* cost, int32_t* status, void* stream);
+
+/* ---- a8 / a12 as single-step batched ops for the StateAGH API (state_agh.py:99-174) --------- */
+typedef struct {
+  const uint8_t* coord; const float* demand; const float* tw_left; const double* tw_right;
+  const double* duration; const float* distance;
+  int64_t* prev_a;        /* [B] */
+  float* used_capacity;   /* [B] */
+  uint8_t* visited;       /* [B][n] */
+  float* lengths;         /* [B] */
+  double* cur_free_time;  /* [B] */
+  float* serve_time;      /* [B][n] */
+  int B, N;
+} agh_state;
+
+int agh_state_get_mask(const agh_state* st, uint8_t* mask /*[B][n], 1 = infeasible*/, void* stream);
+int agh_state_update(const agh_state* st, const int64_t* selected /*[B]*/, void* stream);
+
+/* ---- a16: best-of-R reduction of sample_many (utils/functions.py:190-223) -------------------
+ *   costs[R*B] (replica-major: row r*B+b), pi[R*B][t_stride] i16, serve[R*B][n]
+ *   -> best_cost[B], best_pi[B][t_stride], best_serve[B][n], best_rep[B]
+ */
+int agh_best_of(const float* costs, const int16_t* pi, const float* serve, int R, int B, int N, int t_stride,
+                float* best_cost, int16_t* best_pi, float* best_serve, int32_t* best_rep, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGH_B200_H */
