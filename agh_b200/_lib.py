@@ -1,0 +1,129 @@
+"""ctypes binding of libagh_b200.so (the C ABI declared in include/agh_b200.h).
+
+The library is built in-tree (agh_b200/libagh_b200.so) by `build_library()` /
+`__graft_entry__.build()` with nvcc for sm_100a.  There is NO fallback: if the
+shared object is missing, or a call is made with CPU tensors, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libagh_b200.so')
+CSRC = os.path.join(_HERE, 'csrc')
+SOURCES = ['decode.cu', 'encoder.cu', 'env.cu']
+NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
+              '-std=c++17']
+
+AGH_GREEDY, AGH_SAMPLING, AGH_REPLAY = 0, 1, 2
+AGH_TOUR_INVALID, AGH_CAPACITY_EXCEEDED, AGH_TW_VIOLATED = 1, 2, 4
+KEY_STRIDE = 132
+D = 128
+
+
+class AghError(RuntimeError):
+    pass
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile agh_b200/csrc/*.cu into agh_b200/libagh_b200.so (sm_100a, -lineinfo)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, 'common.cuh'), os.path.join(_HERE, '..', 'include', 'agh_b200.h')]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + srcs
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise AghError('nvcc failed:\n' + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+class DecodeArgs(C.Structure):
+    _fields_ = [
+        ('keys', C.c_void_p), ('psc', C.c_void_p), ('qbase', C.c_void_p), ('coord', C.c_void_p),
+        ('demand', C.c_void_p), ('tw_left', C.c_void_p), ('tw_right', C.c_void_p), ('duration', C.c_void_p),
+        ('distance', C.c_void_p), ('wblob', C.c_void_p),
+        ('key_mod', C.c_int), ('mode', C.c_int), ('temp', C.c_float), ('seed', C.c_uint64), ('id_offset', C.c_int64),
+        ('actions', C.c_void_p), ('replay_steps', C.c_int), ('inject_logp', C.c_void_p), ('t_stride', C.c_int),
+        ('pi', C.c_void_p), ('steps', C.c_void_p), ('ll', C.c_void_p), ('cost', C.c_void_p), ('serve', C.c_void_p),
+        ('logp_sel', C.c_void_p), ('logp_full', C.c_void_p), ('mask_dump', C.c_void_p), ('used_dump', C.c_void_p),
+        ('cft_dump', C.c_void_p), ('B', C.c_int), ('N', C.c_int),
+    ]
+
+
+class StateArgs(C.Structure):
+    _fields_ = [
+        ('coord', C.c_void_p), ('demand', C.c_void_p), ('tw_left', C.c_void_p), ('tw_right', C.c_void_p),
+        ('duration', C.c_void_p), ('distance', C.c_void_p), ('prev_a', C.c_void_p), ('used_capacity', C.c_void_p),
+        ('visited', C.c_void_p), ('lengths', C.c_void_p), ('cur_free_time', C.c_void_p), ('serve_time', C.c_void_p),
+        ('B', C.c_int), ('N', C.c_int),
+    ]
+
+
+# every symbol include/agh_b200.h declares: name -> (restype, argtypes)
+_P, _I = C.c_void_p, C.c_int
+SYMBOLS = {
+    'agh_last_error': (C.c_char_p, []),
+    'agh_version': (_I, []),
+    'agh_launch_count': (C.c_ulonglong, []),
+    'agh_wblob_floats': (C.c_size_t, []),
+    'agh_fleet_task': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'agh_chain_tw_left': (_I, [_P, _I, _P, _I, _I, _P]),
+    'agh_encoder_workspace_bytes': (C.c_size_t, [_I, _I]),
+    'agh_encode': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    'agh_init_embed': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    'agh_encode_layers': (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    'agh_precompute': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    'agh_decode': (_I, [C.POINTER(DecodeArgs), _P]),
+    'agh_get_costs': (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    'agh_state_get_mask': (_I, [C.POINTER(StateArgs), _P, _P]),
+    'agh_state_update': (_I, [C.POINTER(StateArgs), _P, _P]),
+    'agh_best_of': (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Raises AghError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AghError('%s not found: run `python -c "import __graft_entry__ as g; g.build()"` '
+                           '(nvcc, sm_100a). There is no CPU or PyTorch fallback.' % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)          # AttributeError if the symbol is missing
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise AghError('libagh_b200 call failed (%d): %s' % (rc, lib().agh_last_error().decode()))
+
+
+def ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
+    """Device pointer of a contiguous CUDA tensor (None passes NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise AghError('agh_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path' % t.device)
+    if not t.is_contiguous():
+        raise AghError('non-contiguous tensor passed to the C ABI')
+    if dtype is not None and t.dtype != dtype:
+        raise AghError('expected dtype %s, got %s' % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,533 @@
+// Fused persistent decode kernel: one CTA per (instance, fleet) runs ALL decode steps.
+//
+// Replaces, per step, attention_model.py:429-451 (_get_log_p), :510-522 (step context), :550-584
+// (_one_to_many_logits), :372-390 (_select_node), state_agh.py:148-174 (get_mask) and :99-137
+// (update) -- ~93 ATen launches and 4 host syncs per step in the reference -- and accumulates
+// the log-likelihood (attention_model.py:238-250) and the tour length (problem_agh.py:66) on the
+// fly so the [B,T,n] log-prob tensor is never materialised.
+//
+// Data layout:
+//   * the instance's K'/V/LK' rows ([n][132] f32 each, written by agh_precompute) are staged ONCE
+//     into shared memory with cp.async.bulk (TMA bulk copy, mbarrier completion) and stay there
+//     for all T steps; P_sc = W_sc[:, :128] h (the node part of the step-context projection) is
+//     staged too when it fits.  For N >= 200 the matrices that do not fit are read through L2.
+//   * W_out is folded into LK' (LK' = W_out^T W_lk / sqrt(128)), so a step is
+//       q = qbase + P_sc[prev] + w_cap (1-used) + w_time (cft/1440)
+//       s_hj = q_h . K'_jh ; a_h = softmax_j(s_h | mask) ; o_h = sum_j a_hj V_jh
+//       u_j = 10 tanh(o . LK'_j) ; log_p = log_softmax(u / temp | mask)
+//   * 8 warps = 8 heads for the glimpse (warp-local softmax, no block sync), then 16 nodes per
+//     warp for the logits; two __syncthreads per step.
+//   * feasibility mask and state transition follow the reference's mixed f32/f64 arithmetic
+//     exactly (SURVEY.md section 8a numerics contract): f32 table lookup, f32 IEEE division by
+//     110, f64 time accumulation, f32 capacity.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace agh {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+// Philox4x32-10 (Salmon et al. 2011); counter = (instance id lo/hi, step, node), key = seed.
+__device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint64_t id, uint32_t step, uint32_t node) {
+  uint32_t c0 = (uint32_t)id, c1 = (uint32_t)(id >> 32), c2 = step, c3 = node;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+__device__ __forceinline__ float gumbel(uint64_t seed, uint64_t id, uint32_t step, uint32_t node) {
+  const float u = ((float)philox_u32(seed, id, step, node) + 0.5f) * 2.3283064365386963e-10f;  // (0,1)
+  return -logf(-logf(fminf(u, 0.99999994f)));
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+
+template <int NPL>
+__device__ __forceinline__ uint32_t pick_word(const uint32_t (&w)[NPL], int idx) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int p = 0; p < NPL; ++p) r = (idx == p) ? w[p] : r;
+  return r;
+}
+
+struct DecodeSmem {
+  // byte offsets into dynamic shared memory
+  size_t K, V, L, P, twr, dur, twl, dem, crd, dcur, z, serve, o, qb, wc, wt, red, bar, total;
+};
+
+__host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int nsm) {
+  DecodeSmem s;
+  const size_t npad = (size_t)npl * 32;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  s.K = take(nsm >= 1 ? (size_t)n * KS * 4 : 0);
+  s.V = take(nsm >= 2 ? (size_t)n * KS * 4 : 0);
+  s.L = take(nsm >= 3 ? (size_t)n * KS * 4 : 0);
+  s.P = take(nsm >= 4 ? (size_t)n * D * 4 : 0);
+  s.twr = take(npad * 8); s.dur = take(npad * 8);
+  s.twl = take(npad * 4); s.dem = take(npad * 4); s.crd = take(npad * 4);
+  s.dcur = take(2 * npad * 4); s.z = take(npad * 4); s.serve = take(npad * 4);
+  s.o = take(D * 4); s.qb = take(D * 4); s.wc = take(D * 4); s.wt = take(D * 4);
+  s.red = take(8 * 8 * 4);
+  s.bar = take(16);
+  s.total = off;
+  return s;
+}
+
+// NPL: nodes per lane in the glimpse (ceil(n/32)); NSM: how many of {K',V,LK',P_sc} live in smem.
+template <int NPL, int NSM>
+__global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) decode_kernel(const agh_decode_args a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int n = a.N + 1;
+  const int b = blockIdx.x;
+  const int kb = a.key_mod > 0 ? b % a.key_mod : b;      // source of keys / node vectors
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const DecodeSmem L = decode_smem_layout(n, NPL, NSM);
+  constexpr int NPAD = NPL * 32;
+
+  float* sK = reinterpret_cast<float*>(smem + L.K);
+  float* sV = reinterpret_cast<float*>(smem + L.V);
+  float* sL = reinterpret_cast<float*>(smem + L.L);
+  float* sP = reinterpret_cast<float*>(smem + L.P);
+  double* s_twr = reinterpret_cast<double*>(smem + L.twr);
+  double* s_dur = reinterpret_cast<double*>(smem + L.dur);
+  float* s_twl = reinterpret_cast<float*>(smem + L.twl);
+  float* s_dem = reinterpret_cast<float*>(smem + L.dem);
+  int* s_crd = reinterpret_cast<int*>(smem + L.crd);
+  float* s_dcur = reinterpret_cast<float*>(smem + L.dcur);
+  float* s_z = reinterpret_cast<float*>(smem + L.z);
+  float* s_serve = reinterpret_cast<float*>(smem + L.serve);
+  float* s_o = reinterpret_cast<float*>(smem + L.o);
+  float* s_qb = reinterpret_cast<float*>(smem + L.qb);
+  float* s_wc = reinterpret_cast<float*>(smem + L.wc);
+  float* s_wt = reinterpret_cast<float*>(smem + L.wt);
+  float* s_red = reinterpret_cast<float*>(smem + L.red);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+
+  const float* gkeys = a.keys + (size_t)kb * 3 * n * KS;
+  const float* gpsc = a.psc + (size_t)kb * n * D;
+
+  // ---- stage the key matrices with TMA bulk copies (one mbarrier, one phase) ----
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t mat_bytes = (uint32_t)n * KS * 4;
+    uint32_t total = 0;
+    if (NSM >= 1) total += mat_bytes;
+    if (NSM >= 2) total += mat_bytes;
+    if (NSM >= 3) total += mat_bytes;
+    if (NSM >= 4) total += (uint32_t)n * D * 4;
+    mbar_expect_tx(bar, total);
+    if (NSM >= 1) bulk_g2s(sK, gkeys, mat_bytes, bar);
+    if (NSM >= 2) bulk_g2s(sV, gkeys + (size_t)n * KS, mat_bytes, bar);
+    if (NSM >= 3) bulk_g2s(sL, gkeys + (size_t)2 * n * KS, mat_bytes, bar);
+    if (NSM >= 4) bulk_g2s(sP, gpsc, (uint32_t)n * D * 4, bar);
+  }
+  // node vectors and per-instance constants with ordinary loads while the bulk copies fly
+  for (int j = tid; j < NPAD; j += 256) {
+    const bool ok = j < n;
+    s_twr[j] = ok ? a.tw_right[(size_t)kb * n + j] : 0.0;
+    s_dur[j] = ok ? a.duration[(size_t)kb * n + j] : 0.0;
+    s_twl[j] = ok ? a.tw_left[(size_t)kb * n + j] : 0.f;
+    s_dem[j] = (ok && j >= 1) ? a.demand[(size_t)kb * a.N + j - 1] : 0.f;
+    s_crd[j] = ok ? (int)a.coord[(size_t)kb * n + j] : 0;
+    s_serve[j] = 0.f;
+  }
+  if (tid < D) {
+    s_qb[tid] = a.qbase[(size_t)kb * D + tid];
+    s_wc[tid] = a.wblob[W_CAP + tid];
+    s_wt[tid] = a.wblob[W_TIME + tid];
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  const float* Km = NSM >= 1 ? sK : gkeys;
+  const float* Vm = NSM >= 2 ? sV : gkeys + (size_t)n * KS;
+  const float* Lm = NSM >= 3 ? sL : gkeys + (size_t)2 * n * KS;
+  const float* Pm = NSM >= 4 ? sP : gpsc;
+
+  // ---- per-lane node constants (nodes lane + 32p) ----
+  int cj[NPL];
+  float demj[NPL], twlj[NPL];
+  double twrj[NPL], durj[NPL];
+#pragma unroll
+  for (int p = 0; p < NPL; ++p) {
+    const int j = lane + 32 * p;
+    cj[p] = s_crd[j]; demj[p] = s_dem[j]; twlj[p] = s_twl[j]; twrj[p] = s_twr[j]; durj[p] = s_dur[j];
+  }
+
+  // ---- state (replicated in every thread) : state_agh.py:60-93 ----
+  int prev = 0, t = 0, nvis = 0;
+  float used = 0.f, len = 0.f, ll = 0.f;
+  double cft = -60.0;
+  uint32_t vw[NPL];
+#pragma unroll
+  for (int p = 0; p < NPL; ++p) vw[p] = 0u;
+
+  const int h = warp;
+  const bool replay = a.mode == AGH_REPLAY;
+  const uint64_t rng_id = (uint64_t)(a.id_offset + b);
+  const size_t trow = (size_t)b * a.t_stride;
+  const int nwords = (n + 31) / 32;
+
+  while (replay ? (t < a.replay_steps) : (nvis < n)) {
+    const int cprev = s_crd[prev];
+    // (1) distance row of the current location, gathered by the coordinate of my nodes
+    float dd[NPL];
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) dd[p] = (lane + 32 * p < n) ? __ldg(a.distance + NODE_SIZE * cprev + cj[p]) : 0.f;
+
+    // (2) query for my head: attention_model.py:432-435,510-522
+    const float rem = 1.0f - used;
+    const float tf = (float)(cft / 1440.0);
+    float q[HD];
+    {
+      const float4* pr = reinterpret_cast<const float4*>(Pm + (size_t)prev * D + h * HD);
+      const float4* qb4 = reinterpret_cast<const float4*>(s_qb + h * HD);
+      const float4* wc4 = reinterpret_cast<const float4*>(s_wc + h * HD);
+      const float4* wt4 = reinterpret_cast<const float4*>(s_wt + h * HD);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 pv = pr[i], bv = qb4[i], cv = wc4[i], tv = wt4[i];
+        q[4 * i + 0] = fmaf(tv.x, tf, fmaf(cv.x, rem, bv.x + pv.x));
+        q[4 * i + 1] = fmaf(tv.y, tf, fmaf(cv.y, rem, bv.y + pv.y));
+        q[4 * i + 2] = fmaf(tv.z, tf, fmaf(cv.z, rem, bv.z + pv.z));
+        q[4 * i + 3] = fmaf(tv.w, tf, fmaf(cv.w, rem, bv.w + pv.w));
+      }
+    }
+
+    // (3) compatibilities of my nodes with head h (K' already holds the 1/sqrt(16))
+    float s[NPL];
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) {
+      const int j = lane + 32 * p;
+      float acc = 0.f;
+      if (j < n) {
+        const float4* kr = reinterpret_cast<const float4*>(Km + (size_t)j * KS + h * HD);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc = dot4(make_float4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]), kr[i], acc);
+      }
+      s[p] = acc;
+    }
+
+    // (4) feasibility mask: state_agh.py:148-174, exact dtypes
+    bool m[NPL];
+    bool feas_any = false;
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) {
+      const int j = lane + 32 * p;
+      bool mj = true;
+      if (j < n && j >= 1) {
+        const bool cap = __fadd_rn(demj[p], used) > 1.0f;
+        const float tt = __fdiv_rn(dd[p], 110.0f);
+        const double fin = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)twlj[p]), durj[p]);
+        const bool tw = fin > twrj[p];
+        mj = ((vw[p] >> lane) & 1u) | cap | tw;
+        feas_any |= !mj;
+      }
+      m[p] = mj;
+    }
+    const bool anyf = __any_sync(0xffffffffu, feas_any);
+    if (lane == 0) m[0] = (prev == 0) && anyf;      // depot: state_agh.py:173
+    uint32_t mw[NPL];
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) mw[p] = __ballot_sync(0xffffffffu, m[p]);
+    if (warp == 0) {
+      float* dc = s_dcur + (t & 1) * NPAD;
+#pragma unroll
+      for (int p = 0; p < NPL; ++p) dc[lane + 32 * p] = dd[p];
+      if (a.mask_dump != nullptr && lane < nwords) a.mask_dump[(trow + t) * nwords + lane] = pick_word<NPL>(mw, lane);
+      if (lane == 0) {
+        if (a.used_dump != nullptr) a.used_dump[trow + t] = used;
+        if (a.cft_dump != nullptr) a.cft_dump[trow + t] = cft;
+      }
+    }
+
+    // (5) masked softmax over the nodes, warp-local: attention_model.py:559-565
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) {
+      s[p] = m[p] ? -CUDART_INF_F : s[p];
+      mx = fmaxf(mx, s[p]);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float e[NPL], esum = 0.f;
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) {
+      e[p] = m[p] ? 0.f : expf(s[p] - mx);
+      esum += e[p];
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, off);
+
+    // (6) o_h = sum_j a_j V_jh, butterfly transpose-reduce over the 32 lanes
+    float acc[HD];
+#pragma unroll
+    for (int k = 0; k < HD; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) {
+      const int j = lane + 32 * p;
+      if (j < n) {
+        const float4* vr = reinterpret_cast<const float4*>(Vm + (size_t)j * KS + h * HD);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = vr[i];
+          acc[4 * i + 0] = fmaf(e[p], v.x, acc[4 * i + 0]);
+          acc[4 * i + 1] = fmaf(e[p], v.y, acc[4 * i + 1]);
+          acc[4 * i + 2] = fmaf(e[p], v.z, acc[4 * i + 2]);
+          acc[4 * i + 3] = fmaf(e[p], v.w, acc[4 * i + 3]);
+        }
+      }
+    }
+    {
+      float r8[8], r4[4], r2[2], r1;
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float send = b4 ? acc[k] : acc[k + 8], keep = b4 ? acc[k + 8] : acc[k];
+        r8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float send = b3 ? r8[k] : r8[k + 4], keep = b3 ? r8[k + 4] : r8[k];
+        r4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float send = b2 ? r4[k] : r4[k + 2], keep = b2 ? r4[k + 2] : r4[k];
+        r2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      {
+        const float send = b1 ? r2[0] : r2[1], keep = b1 ? r2[1] : r2[0];
+        r1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+      // lane now owns element (b4 b3 b2 b1) = 8*b4 + 4*b3 + 2*b2 + b1 of o_h
+      if ((lane & 1) == 0) s_o[h * HD + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] =
+          __fdiv_rn(r1, esum);
+    }
+    __syncthreads();   // (A) o complete
+
+    // (7) logits for 16 nodes per warp and pass; lanes 0-15 take features 0..63, lanes 16-31 64..127
+    const int half = lane >> 4, jj = lane & 15;
+    constexpr int NPASS = (NPL * 32 + 127) / 128;
+    float zp[NPASS], scp[NPASS];
+    float wm = -CUDART_INF_F;
+    float best_sc = -CUDART_INF_F, best_z = 0.f;
+    int best_j = 0x7fffffff;
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ++ps) {
+      const int j = ps * 128 + warp * 16 + jj;
+      float u = 0.f;
+      if (j < n) {
+        const float4* lr = reinterpret_cast<const float4*>(Lm + (size_t)j * KS + half * 64);
+        const float4* o4 = reinterpret_cast<const float4*>(s_o + half * 64);
+        float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          u0 = dot4(o4[i], lr[i], u0);
+          u1 = dot4(o4[i + 1], lr[i + 1], u1);
+        }
+        u = u0 + u1;
+      }
+      u += __shfl_xor_sync(0xffffffffu, u, 16);
+      const bool mj = (j >= n) || ((pick_word<NPL>(mw, j >> 5) >> (j & 31)) & 1u);
+      float z = -CUDART_INF_F;
+      if (!mj) z = __fdiv_rn(10.0f * tanhf(u), a.temp);      // attention_model.py:580, :447
+      if (half == 0 && j < n) s_z[j] = z;
+      float sc = z;
+      if (a.inject_logp != nullptr) {
+        sc = (j < n) ? expf(__ldg(a.inject_logp + (trow + t) * n + j)) : -CUDART_INF_F;   // argmax(exp(log_p)), :333,:377
+      } else if (a.mode == AGH_SAMPLING && !mj) {
+        sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
+      }
+      zp[ps] = (half == 0) ? z : -CUDART_INF_F;
+      scp[ps] = sc;
+      wm = fmaxf(wm, zp[ps]);
+      if (half == 0 && sc > best_sc) { best_sc = sc; best_j = j; best_z = z; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+    float ws = 0.f;
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ++ps) ws += (zp[ps] == -CUDART_INF_F) ? 0.f : expf(zp[ps] - wm);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      ws += __shfl_xor_sync(0xffffffffu, ws, off);
+      const float osc = __shfl_xor_sync(0xffffffffu, best_sc, off);
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j, off);
+      const float oz = __shfl_xor_sync(0xffffffffu, best_z, off);
+      if (osc > best_sc || (osc == best_sc && oj < best_j)) { best_sc = osc; best_j = oj; best_z = oz; }
+    }
+    if (lane == 0) {
+      float4* r = reinterpret_cast<float4*>(s_red + warp * 8);
+      r[0] = make_float4(wm, ws, best_sc, __int_as_float(best_j));
+      r[1] = make_float4(best_z, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();   // (B) per-warp partials complete
+
+    // (8) merge, select, update (every thread, redundantly): attention_model.py:446-447,372-390; state_agh.py:99-137
+    float M = -CUDART_INF_F;
+    float g_sc = -CUDART_INF_F, g_z = 0.f;
+    int sel = 0x7fffffff;
+    float wms[8], wss[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float4 r0 = reinterpret_cast<const float4*>(s_red + w * 8)[0];
+      const float4 r1v = reinterpret_cast<const float4*>(s_red + w * 8)[1];
+      wms[w] = r0.x; wss[w] = r0.y;
+      M = fmaxf(M, r0.x);
+      const int oj = __float_as_int(r0.w);
+      if (r0.z > g_sc || (r0.z == g_sc && oj < sel)) { g_sc = r0.z; sel = oj; g_z = r1v.x; }
+    }
+    float S = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) S += (wms[w] == -CUDART_INF_F) ? 0.f : wss[w] * expf(wms[w] - M);
+    const float logS = logf(S);
+    if (replay) {
+      sel = (int)a.actions[trow + t];
+      g_z = s_z[sel];
+    }
+    const float lp = (g_z - M) - logS;
+    ll += lp;
+    if (a.logp_full != nullptr) {
+      for (int j = tid; j < n; j += 256) a.logp_full[(trow + t) * n + j] = (s_z[j] - M) - logS;
+    }
+
+    const float d = s_dcur[(t & 1) * NPAD + sel];
+    len = __fadd_rn(len, d);
+    if (sel != 0) {
+      used = __fadd_rn(used, s_dem[sel]);
+      const float tt = __fdiv_rn(d, 110.0f);
+      cft = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)s_twl[sel]), s_dur[sel]);
+    } else {
+      used = 0.f;
+      cft = -60.0;
+    }
+    {
+      const uint32_t bit = 1u << (sel & 31);
+      const int wsel = sel >> 5;
+#pragma unroll
+      for (int p = 0; p < NPL; ++p) {
+        if (wsel == p) { nvis += (vw[p] & bit) ? 0 : 1; vw[p] |= bit; }
+      }
+    }
+    if (tid == 0) {
+      s_serve[sel] = (float)cft;
+      a.pi[trow + t] = (int16_t)sel;
+      if (a.logp_sel != nullptr) a.logp_sel[trow + t] = lp;
+    }
+    prev = sel;
+    ++t;
+  }
+
+  // ---- epilogue: closed-tour length (problem_agh.py:49-50,66), outputs, zero padding ----
+  __syncthreads();
+  if (tid == 0) {
+    const float back = __ldg(a.distance + NODE_SIZE * s_crd[prev]);
+    a.cost[b] = __fadd_rn(len, back);
+    a.ll[b] = ll;
+    a.steps[b] = t;
+  }
+  for (int j = tid; j < n; j += 256) a.serve[(size_t)b * n + j] = s_serve[j];
+  for (int k = t + tid; k < a.t_stride; k += 256) {
+    a.pi[trow + k] = 0;
+    if (a.logp_sel != nullptr) a.logp_sel[trow + k] = 0.f;
+  }
+}
+
+template <int NPL, int NSM>
+static int launch_decode(const agh_decode_args& a, cudaStream_t st) {
+  const int n = a.N + 1;
+  const DecodeSmem L = decode_smem_layout(n, NPL, NSM);
+  auto kern = decode_kernel<NPL, NSM>;
+  AGH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  kern<<<a.B, 256, L.total, st>>>(a);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+template <int NPL>
+static int dispatch_nsm(const agh_decode_args& a, cudaStream_t st) {
+  const int n = a.N + 1;
+  int dev = 0, max_smem = 0;
+  AGH_CUDA(cudaGetDevice(&dev));
+  AGH_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if ((int)decode_smem_layout(n, NPL, 4).total <= max_smem) return launch_decode<NPL, 4>(a, st);
+  if ((int)decode_smem_layout(n, NPL, 3).total <= max_smem) return launch_decode<NPL, 3>(a, st);
+  if ((int)decode_smem_layout(n, NPL, 2).total <= max_smem) return launch_decode<NPL, 2>(a, st);
+  if ((int)decode_smem_layout(n, NPL, 1).total <= max_smem) return launch_decode<NPL, 1>(a, st);
+  set_error("agh_decode: N=%d does not fit shared memory (%d bytes available)", a.N, max_smem);
+  return AGH_E_UNSUPPORTED;
+}
+
+}  // namespace agh
+
+extern "C" int agh_decode(const agh_decode_args* args, void* stream) {
+  using namespace agh;
+  AGH_CHECK_ARG(args != nullptr);
+  const agh_decode_args& a = *args;
+  AGH_CHECK_ARG(a.B >= 0 && a.N >= 1 && a.N <= AGH_MAX_N - 1);
+  if (a.B == 0) return AGH_OK;
+  AGH_CHECK_ARG(a.keys && a.psc && a.qbase && a.coord && a.demand && a.tw_left && a.tw_right && a.duration);
+  AGH_CHECK_ARG(a.distance && a.wblob && a.pi && a.steps && a.ll && a.cost && a.serve);
+  AGH_CHECK_ARG(a.mode == AGH_GREEDY || a.mode == AGH_SAMPLING || a.mode == AGH_REPLAY);
+  AGH_CHECK_ARG(a.mode != AGH_REPLAY || (a.actions != nullptr && a.replay_steps >= 0 && a.replay_steps <= a.t_stride));
+  AGH_CHECK_ARG(a.t_stride >= 2 * a.N - 1 && a.t_stride >= 1);
+  AGH_CHECK_ARG(a.temp > 0.f);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int npl = ceil_div(a.N + 1, 32);
+  switch (npl) {
+    case 1: return dispatch_nsm<1>(a, st);
+    case 2: return dispatch_nsm<2>(a, st);
+    case 3: return dispatch_nsm<3>(a, st);
+    case 4: return dispatch_nsm<4>(a, st);
+    case 5: return dispatch_nsm<5>(a, st);
+    case 6: return dispatch_nsm<6>(a, st);
+    case 7: return dispatch_nsm<7>(a, st);
+    case 8: return dispatch_nsm<8>(a, st);
+    case 9: return dispatch_nsm<9>(a, st);
+    case 10: return dispatch_nsm<10>(a, st);
+    default: break;
+  }
+  set_error("agh_decode: N=%d unsupported", a.N);
+  return AGH_E_UNSUPPORTED;
+}

@@ -1,0 +1,351 @@
+// Graph-attention encoder (eval-mode BatchNorm) and decoder precompute, fp32 CUDA-core path.
+//
+//   agh_init_embed : attention_model.py:272-294
+//   agh_encode     : graph_encoder.py:56-111 (MHA), :135-143 (BatchNorm1d, running stats),
+//                    :146-172 (layer = MHA+skip, BN, FF+skip, BN), :195-207
+//   agh_precompute : attention_model.py:392-414, :604-611
+//
+// All dense contractions go through one tiled SGEMM (128x128x16 tiles, 8x8 register micro-tile,
+// register double buffering) whose epilogue fuses bias / ReLU / residual + BatchNorm scale-shift /
+// the scatter into the padded key layout the decode kernel stages with TMA.  Self-attention is a
+// flash-style kernel: one CTA per (instance, head), K_h/V_h staged in shared memory, one query row
+// per thread with an online softmax, so no [n,n] score matrix ever reaches HBM.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace agh {
+
+// ------------------------------------------------------------------------------------------
+// init embedding
+// ------------------------------------------------------------------------------------------
+__global__ void init_embed_kernel(const float* __restrict__ w, const uint8_t* __restrict__ coord,
+                                  const float* __restrict__ demand, const float* __restrict__ tw_left,
+                                  const double* __restrict__ tw_right, int twr_f32, int B, int N, float* __restrict__ h0) {
+  const int n = N + 1;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 4 columns)
+  const size_t total = (size_t)B * n * (D / 4);
+  if (idx >= total) return;
+  const int c4 = (int)(idx % (D / 4));
+  const size_t row = idx / (D / 4);
+  const int j = (int)(row % n);
+  const size_t b = row / n;
+  const int loc = coord[row];
+  float4 v = reinterpret_cast<const float4*>(w + W_LOC_EMB + (size_t)loc * D)[c4];
+  if (j >= 1) {
+    // features are concatenated in f64 when tw_right is f64 and then cast to f32
+    // (attention_model.py:290-292): demand and tw_left/1440 are f32 values, tw_right/1440 is an
+    // f64 division rounded to f32 (an f32 division when tw_right is f32: fleet 10).
+    const float f0 = demand[b * N + (j - 1)];
+    const float f1 = __fdiv_rn(tw_left[row], 1440.0f);
+    const float f2 = twr_f32 ? __fdiv_rn((float)tw_right[row], 1440.0f) : (float)(tw_right[row] / 1440.0);
+    const float4 w0 = reinterpret_cast<const float4*>(w + W_INIT_W)[c4];
+    const float4 w1 = reinterpret_cast<const float4*>(w + W_INIT_W + D)[c4];
+    const float4 w2 = reinterpret_cast<const float4*>(w + W_INIT_W + 2 * D)[c4];
+    const float4 bb = reinterpret_cast<const float4*>(w + W_INIT_B)[c4];
+    v.x += fmaf(w2.x, f2, fmaf(w1.x, f1, fmaf(w0.x, f0, bb.x)));
+    v.y += fmaf(w2.y, f2, fmaf(w1.y, f1, fmaf(w0.y, f0, bb.y)));
+    v.z += fmaf(w2.z, f2, fmaf(w1.z, f1, fmaf(w0.z, f0, bb.z)));
+    v.w += fmaf(w2.w, f2, fmaf(w1.w, f1, fmaf(w0.w, f0, bb.w)));
+  }
+  reinterpret_cast<float4*>(h0 + row * D)[c4] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// SGEMM  C[M,Nc] = epi(A[M,K] @ W[K,Nc])
+// ------------------------------------------------------------------------------------------
+enum { EPI_PLAIN = 0, EPI_BIAS_RELU = 1, EPI_RES_BN = 2, EPI_DEC = 3 };
+
+struct GemmArgs {
+  const float* A; int lda;
+  const float* W;          // [K][Nc] row-major
+  float* C; int ldc;
+  int M, K, Nc;
+  const float* bias;       // [Nc] or null
+  const float* res; int ldr;   // residual
+  const float* bn_s; const float* bn_t;
+  // EPI_DEC
+  float* keys; float* psc; int n;
+};
+
+constexpr int BM = 128, BN = 128, BK = 16, LDA_S = BM + 4;
+
+template <int EPI>
+__global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float As[2][BK][LDA_S];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  // global -> register staging
+  const int a_row = tid >> 2, a_k = (tid & 3) * 4;          // rows a_row, a_row+64
+  const int b_k = tid >> 5, b_n = (tid & 31) * 4;           // k rows b_k, b_k+8
+  float4 ra[2], rb[2];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = m0 + a_row + 64 * i;
+      ra[i] = (r < g.M) ? *reinterpret_cast<const float4*>(g.A + (size_t)r * g.lda + k0 + a_k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[i] = *reinterpret_cast<const float4*>(g.W + (size_t)(k0 + b_k + 8 * i) * g.Nc + n0 + b_n);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = a_row + 64 * i;
+      As[buf][a_k + 0][r] = ra[i].x; As[buf][a_k + 1][r] = ra[i].y; As[buf][a_k + 2][r] = ra[i].z; As[buf][a_k + 3][r] = ra[i].w;
+      *reinterpret_cast<float4*>(&Bs[buf][b_k + 8 * i][b_n]) = rb[i];
+    }
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  const int nk = g.K / BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int col = n0 + jh * 64 + tx * 4;
+      float4 v = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+      if (EPI == EPI_BIAS_RELU) {
+        const float4 bb = *reinterpret_cast<const float4*>(g.bias + col);
+        v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f); v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
+      } else if (EPI == EPI_RES_BN) {
+        if (g.bias != nullptr) {
+          const float4 bb = *reinterpret_cast<const float4*>(g.bias + col);
+          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        }
+        const float4 r = *reinterpret_cast<const float4*>(g.res + (size_t)row * g.ldr + col);
+        const float4 s = *reinterpret_cast<const float4*>(g.bn_s + col);
+        const float4 t = *reinterpret_cast<const float4*>(g.bn_t + col);
+        v.x = fmaf(r.x + v.x, s.x, t.x); v.y = fmaf(r.y + v.y, s.y, t.y);
+        v.z = fmaf(r.z + v.z, s.z, t.z); v.w = fmaf(r.w + v.w, s.w, t.w);
+      }
+      if (EPI == EPI_DEC) {
+        if (col < 3 * D) {
+          const int mat = col / D, c = col % D;
+          const int bi = row / g.n, j = row % g.n;
+          *reinterpret_cast<float4*>(g.keys + (((size_t)bi * 3 + mat) * g.n + j) * KS + c) = v;
+        } else {
+          *reinterpret_cast<float4*>(g.psc + (size_t)row * D + (col - 3 * D)) = v;
+        }
+      } else {
+        *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + col) = v;
+      }
+    }
+  }
+}
+
+template <int EPI>
+static int launch_gemm(const GemmArgs& g, cudaStream_t st) {
+  dim3 grid(ceil_div(g.M, BM), g.Nc / BN);
+  sgemm_kernel<EPI><<<grid, 256, 0, st>>>(g);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// self-attention, one CTA per (instance, head): graph_encoder.py:83-104
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mha_kernel(const float* __restrict__ qkv, int n, float* __restrict__ heads) {
+  extern __shared__ __align__(16) float sm[];
+  float4* sKh = reinterpret_cast<float4*>(sm);               // [n][4] float4
+  float4* sVh = sKh + (size_t)n * 4;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const float* base = qkv + (size_t)b * n * (3 * D);
+  for (int idx = threadIdx.x; idx < n * 4; idx += blockDim.x) {
+    const int j = idx >> 2, c = idx & 3;
+    sKh[idx] = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * D + D + h * HD + c * 4);
+    sVh[idx] = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * D + 2 * D + h * HD + c * 4);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float q[HD];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)i * 3 * D + h * HD + c * 4);
+      q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
+    }
+    float m = -CUDART_INF_F, l = 0.f, o[HD];
+#pragma unroll
+    for (int k = 0; k < HD; ++k) o[k] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < n; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 kv = sKh[j * 4 + c];
+        s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s); s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
+      }
+      s *= 0.25f;                                  // norm_factor = 1/sqrt(16), graph_encoder.py:40,89
+      if (s > m) {
+        const float c0 = expf(m - s);
+        l *= c0;
+#pragma unroll
+        for (int k = 0; k < HD; ++k) o[k] *= c0;
+        m = s;
+      }
+      const float p = expf(s - m);
+      l += p;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 vv = sVh[j * 4 + c];
+        o[4 * c] = fmaf(p, vv.x, o[4 * c]); o[4 * c + 1] = fmaf(p, vv.y, o[4 * c + 1]);
+        o[4 * c + 2] = fmaf(p, vv.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(p, vv.w, o[4 * c + 3]);
+      }
+    }
+    const float inv = 1.0f / l;
+    float* out = heads + ((size_t)b * n + i) * D + h * HD;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(out + 4 * c) = make_float4(o[4 * c] * inv, o[4 * c + 1] * inv, o[4 * c + 2] * inv, o[4 * c + 3] * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// qbase = W_fc mean_n(h) + fleet_emb : attention_model.py:395-402
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) qbase_kernel(const float* __restrict__ w, const float* __restrict__ h,
+                                                    const int32_t* __restrict__ fleet_ids, int fleet, int n,
+                                                    float* __restrict__ qbase) {
+  __shared__ float mean[D];
+  const int b = blockIdx.x, c = threadIdx.x;
+  float s = 0.f;
+  for (int j = 0; j < n; ++j) s += h[((size_t)b * n + j) * D + c];
+  mean[c] = s / (float)n;
+  __syncthreads();
+  float acc = 0.f;
+  const float* wfc = w + W_FC_T;
+#pragma unroll 8
+  for (int e = 0; e < D; ++e) acc = fmaf(wfc[(size_t)e * D + c], mean[e], acc);
+  const int f = fleet_ids != nullptr ? fleet_ids[b] : fleet;
+  qbase[(size_t)b * D + c] = acc + w[W_FLEET + (size_t)f * D + c];
+}
+
+}  // namespace agh
+
+using namespace agh;
+
+extern "C" size_t agh_encoder_workspace_bytes(int B, int N) {
+  // qkv [M][384] + heads [M][128] + x1 [M][128] + hidden [M][512] + xa [M][128]
+  const size_t M = (size_t)B * (N + 1);
+  return M * (3 * D + D + D + FF + D) * sizeof(float) + 256;
+}
+
+extern "C" int agh_init_embed(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
+                              const double* tw_right, int twr_f32, int B, int N, float* h0, void* stream) {
+  AGH_CHECK_ARG(wblob && coord && demand && tw_left && tw_right && h0 && B >= 0 && N >= 1);
+  if (B == 0) return AGH_OK;
+  const size_t total = (size_t)B * (N + 1) * (D / 4);
+  init_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wblob, coord, demand, tw_left, tw_right,
+                                                                                     twr_f32, B, N, h0);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int N, float* h_out, void* workspace,
+                                 void* stream) {
+  AGH_CHECK_ARG(wblob && h0 && h_out && workspace && B >= 0 && N >= 1 && N < AGH_MAX_N);
+  if (B == 0) return AGH_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = N + 1;
+  const int M = B * n;
+  float* qkv = reinterpret_cast<float*>(workspace);
+  float* heads = qkv + (size_t)M * 3 * D;
+  float* x1 = heads + (size_t)M * D;
+  float* hid = x1 + (size_t)M * D;
+  float* xa = hid + (size_t)M * FF;
+  const float* x = h0;
+  const int mha_threads = n >= 128 ? 128 : 32 * ceil_div(n, 32);
+  const size_t mha_smem = (size_t)n * 2 * HD * sizeof(float);
+  if (mha_smem > 48 * 1024) AGH_CUDA(cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mha_smem));
+  for (int l = 0; l < LAYERS; ++l) {
+    const float* lw = wblob + W_LAYER0 + (size_t)l * L_SIZE;
+    float* xout = (l == LAYERS - 1) ? h_out : xa;
+    GemmArgs g{};
+    g.A = x; g.lda = D; g.W = lw + L_WQKV; g.C = qkv; g.ldc = 3 * D; g.M = M; g.K = D; g.Nc = 3 * D;
+    int rc = launch_gemm<EPI_PLAIN>(g, st);
+    if (rc) return rc;
+    mha_kernel<<<B * H, mha_threads, mha_smem, st>>>(qkv, n, heads);
+    AGH_LAUNCH_CHECK();
+    g = GemmArgs{};
+    g.A = heads; g.lda = D; g.W = lw + L_WO; g.C = x1; g.ldc = D; g.M = M; g.K = D; g.Nc = D;
+    g.res = x; g.ldr = D; g.bn_s = lw + L_BN1S; g.bn_t = lw + L_BN1T;
+    rc = launch_gemm<EPI_RES_BN>(g, st);
+    if (rc) return rc;
+    g = GemmArgs{};
+    g.A = x1; g.lda = D; g.W = lw + L_W1T; g.C = hid; g.ldc = FF; g.M = M; g.K = D; g.Nc = FF; g.bias = lw + L_B1;
+    rc = launch_gemm<EPI_BIAS_RELU>(g, st);
+    if (rc) return rc;
+    g = GemmArgs{};
+    g.A = hid; g.lda = FF; g.W = lw + L_W2T; g.C = xout; g.ldc = D; g.M = M; g.K = FF; g.Nc = D; g.bias = lw + L_B2;
+    g.res = x1; g.ldr = D; g.bn_s = lw + L_BN2S; g.bn_t = lw + L_BN2T;
+    rc = launch_gemm<EPI_RES_BN>(g, st);
+    if (rc) return rc;
+    x = xout;
+  }
+  return AGH_OK;
+}
+
+extern "C" int agh_encode(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
+                          const double* tw_right, int twr_f32, int B, int N, float* h_out, void* workspace, void* stream) {
+  AGH_CHECK_ARG(h_out != nullptr);
+  // h_out doubles as the h0 buffer: layer 0 only reads it before the last layer writes it
+  // (x -> xa -> xa ... -> h_out; with 3 layers h0 must not alias h_out, so keep it in the workspace tail)
+  AGH_CHECK_ARG(workspace != nullptr);
+  const size_t M = (size_t)B * (N + 1);
+  float* h0 = reinterpret_cast<float*>(workspace) + M * (3 * D + D + D + FF);   // == xa slot; layer 0 reads it, layer 0's FF2 overwrites xa
+  (void)h0;
+  // layer 0 reads x=h0 for the QKV GEMM and as the residual of the out-projection, and writes
+  // xa only in its last GEMM, whose inputs are hid and x1 -- so h0 may live in the xa slot.
+  int rc = agh_init_embed(wblob, coord, demand, tw_left, tw_right, twr_f32, B, N, h0, stream);
+  if (rc) return rc;
+  return agh_encode_layers(wblob, h0, B, N, h_out, workspace, stream);
+}
+
+extern "C" int agh_precompute(const float* wblob, const float* h, const int32_t* fleet_ids, int fleet, int B, int N,
+                              float* keys, float* psc, float* qbase, void* stream) {
+  AGH_CHECK_ARG(wblob && h && keys && psc && qbase && B >= 0 && N >= 1);
+  AGH_CHECK_ARG(fleet_ids != nullptr || (fleet >= 0 && fleet < 10));
+  if (B == 0) return AGH_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = N + 1;
+  GemmArgs g{};
+  g.A = h; g.lda = D; g.W = wblob + W_DEC; g.M = B * n; g.K = D; g.Nc = 4 * D; g.keys = keys; g.psc = psc; g.n = n;
+  int rc = launch_gemm<EPI_DEC>(g, st);
+  if (rc) return rc;
+  qbase_kernel<<<B, D, 0, st>>>(wblob, h, fleet_ids, fleet, n, qbase);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}

@@ -1,0 +1,276 @@
+// AGH environment pieces outside the fused decode kernel: fleet-batch assembly (a1), cross-fleet
+// time-window chaining, tour validation + cost (a13), single-step mask/update for the StateAGH API
+// (a8/a12) and the best-of-R reduction of sample_many (a16).  Arithmetic follows the reference's
+// dtypes exactly: f32 distance lookup and f32 IEEE division by SPEED, f64 time
+// accumulation, f32 capacity.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace agh {
+
+static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- a1: train.py:40-57 ----
+__global__ void fleet_task_kernel(const int64_t* __restrict__ loc, const int64_t* __restrict__ type,
+                                  const float* __restrict__ departure, const float* __restrict__ demand_all,
+                                  const float* __restrict__ twl_level, int fleet, double d0, double d1, double d2,
+                                  double nd0, double nd1, double nd2, int nd_is_f32, int B, int N,
+                                  uint8_t* __restrict__ coord, float* __restrict__ demand, float* __restrict__ tw_left,
+                                  double* __restrict__ tw_right, double* __restrict__ duration) {
+  const int n = N + 1;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * n) return;
+  const int j = (int)(idx % n);
+  const size_t b = idx / n;
+  if (j == 0) {
+    coord[idx] = 0; tw_left[idx] = 0.f; tw_right[idx] = 1441.0; duration[idx] = 0.0;
+    return;
+  }
+  const size_t src = b * N + (j - 1);
+  const int ty = (int)type[src];
+  coord[idx] = (uint8_t)loc[src];
+  demand[src] = demand_all[(b * 10 + (fleet - 1)) * N + (j - 1)];
+  tw_left[idx] = twl_level[src];
+  const double nd = ty == 0 ? nd0 : (ty == 1 ? nd1 : nd2);
+  // departure (f32) - next_duration: f64 arithmetic, or f32 when the level's list holds python floats
+  tw_right[idx] = nd_is_f32 ? (double)__fsub_rn(departure[src], (float)nd) : __dsub_rn((double)departure[src], nd);
+  duration[idx] = ty == 0 ? d0 : (ty == 1 ? d1 : d2);
+}
+
+// train.py:67
+__global__ void chain_kernel(float* __restrict__ lvl, const float* __restrict__ serve, int B, int N) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * N) return;
+  const size_t b = idx / N;
+  const int j = (int)(idx % N);
+  lvl[idx] = fmaxf(lvl[idx], serve[b * (N + 1) + j + 1]);
+}
+
+// ---- a13: problem_agh.py:18-66, one warp per instance ----
+template <typename PiT>
+__global__ void get_costs_kernel(const PiT* __restrict__ pi, int T, const uint8_t* __restrict__ coord,
+                                 const float* __restrict__ demand, const float* __restrict__ tw_left,
+                                 const double* __restrict__ tw_right, const double* __restrict__ duration,
+                                 const float* __restrict__ dist, int B, int N, float* __restrict__ cost,
+                                 int32_t* __restrict__ status) {
+  const int n = N + 1;
+  const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const PiT* p = pi + (size_t)b * T;
+  int st = 0;
+  // (1) tour is zeros plus a permutation of 1..N (problem_agh.py:21-27): count visits per node
+  int bad = 0;
+  for (int j = 1 + lane; j <= N; j += 32) {
+    int cnt = 0;
+    for (int t = 0; t < T; ++t) cnt += (p[t] == j);
+    bad |= (cnt != 1);
+  }
+  for (int t = lane; t < T; t += 32) bad |= (p[t] < 0 || p[t] > N);
+  if (__any_sync(0xffffffffu, bad)) st |= AGH_TOUR_INVALID;
+  if (st) {                         // indices are not safe to replay
+    if (lane == 0) { status[b] = st; cost[b] = 0.f; }
+    return;
+  }
+  // (2)+(3) sequential replay by lane 0
+  if (lane == 0) {
+    float used = 0.f, total = 0.f;
+    double cur = -60.0;
+    int prev_c = 0;
+    for (int t = 0; t < T; ++t) {
+      const int a = (int)p[t];
+      const float dem = a == 0 ? -1.0f : demand[(size_t)b * N + a - 1];
+      used = __fadd_rn(used, dem);
+      if (used < 0.f) used = 0.f;
+      if (!(used <= 1.0f + 1e-5f)) st |= AGH_CAPACITY_EXCEEDED;
+      const int c = coord[(size_t)b * n + a];
+      const float d = dist[NODE_SIZE * prev_c + c];
+      total = __fadd_rn(total, d);
+      if (a != 0) {
+        // first step: cur_time is int64 -60 (problem_agh.py:58) so the sum is f32; identical result
+        const float tt = __fdiv_rn(d, 110.0f);
+        cur = __dadd_rn(fmax(__dadd_rn(cur, (double)tt), (double)tw_left[(size_t)b * n + a]), duration[(size_t)b * n + a]);
+      } else {
+        cur = -60.0;
+      }
+      if (!(cur <= tw_right[(size_t)b * n + a] + 1e-5)) st |= AGH_TW_VIOLATED;
+      prev_c = c;
+    }
+    total = __fadd_rn(total, dist[NODE_SIZE * prev_c]);
+    cost[b] = total;
+    status[b] = st;
+  }
+}
+
+// ---- a8: state_agh.py:148-174, one thread per (instance, node) + one block-free depot pass ----
+__global__ void state_mask_kernel(const agh_state st, uint8_t* __restrict__ mask) {
+  const int n = st.N + 1;
+  const int b = blockIdx.x;
+  __shared__ int any_feasible;
+  if (threadIdx.x == 0) any_feasible = 0;
+  __syncthreads();
+  const int prev = (int)st.prev_a[b];
+  const int cprev = st.coord[(size_t)b * n + prev];
+  const float used = st.used_capacity[b];
+  const double cft = st.cur_free_time[b];
+  int feas = 0;
+  for (int j = 1 + threadIdx.x; j < n; j += blockDim.x) {
+    const size_t k = (size_t)b * n + j;
+    const bool cap = __fadd_rn(st.demand[(size_t)b * st.N + j - 1], used) > 1.0f;
+    const float tt = __fdiv_rn(st.distance[NODE_SIZE * cprev + st.coord[k]], 110.0f);
+    const double fin = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)st.tw_left[k]), st.duration[k]);
+    const bool m = st.visited[k] | cap | (fin > st.tw_right[k]);
+    mask[k] = m;
+    feas |= !m;
+  }
+  if (feas) atomicOr(&any_feasible, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) mask[(size_t)b * n] = (prev == 0) && any_feasible;
+}
+
+// ---- a12: state_agh.py:99-137 ----
+__global__ void state_update_kernel(const agh_state st, const int64_t* __restrict__ selected) {
+  const int n = st.N + 1;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= st.B) return;
+  const int sel = (int)selected[b];
+  const int prev = (int)st.prev_a[b];
+  const float d = st.distance[NODE_SIZE * st.coord[(size_t)b * n + prev] + st.coord[(size_t)b * n + sel]];
+  st.lengths[b] = __fadd_rn(st.lengths[b], d);
+  double cft;
+  if (sel != 0) {
+    st.used_capacity[b] = __fadd_rn(st.used_capacity[b], st.demand[(size_t)b * st.N + sel - 1]);
+    const float tt = __fdiv_rn(d, 110.0f);
+    cft = __dadd_rn(fmax(__dadd_rn(st.cur_free_time[b], (double)tt), (double)st.tw_left[(size_t)b * n + sel]),
+                    st.duration[(size_t)b * n + sel]);
+  } else {
+    st.used_capacity[b] = 0.f;
+    cft = -60.0;
+  }
+  st.cur_free_time[b] = cft;
+  st.visited[(size_t)b * n + sel] = 1;
+  st.serve_time[(size_t)b * n + sel] = (float)cft;
+  st.prev_a[b] = sel;
+}
+
+// ---- a16: utils/functions.py:216-219, first minimum over replicas ----
+__global__ void best_of_kernel(const float* __restrict__ costs, const int16_t* __restrict__ pi, const float* __restrict__ serve,
+                               int R, int B, int n, int t_stride, float* __restrict__ best_cost,
+                               int16_t* __restrict__ best_pi, float* __restrict__ best_serve, int32_t* __restrict__ best_rep) {
+  const int b = blockIdx.x;
+  __shared__ float s_c[32];
+  __shared__ int s_r[32];
+  float bc = INFINITY;
+  int br = 0x7fffffff;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const float c = costs[(size_t)r * B + b];
+    if (c < bc) { bc = c; br = r; }
+  }
+  for (int off = 16; off >= 1; off >>= 1) {
+    const float oc = __shfl_xor_sync(0xffffffffu, bc, off);
+    const int orr = __shfl_xor_sync(0xffffffffu, br, off);
+    if (oc < bc || (oc == bc && orr < br)) { bc = oc; br = orr; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = bc; s_r[threadIdx.x >> 5] = br; }
+  __syncthreads();
+  bc = s_c[0]; br = s_r[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+    if (s_c[w] < bc || (s_c[w] == bc && s_r[w] < br)) { bc = s_c[w]; br = s_r[w]; }
+  if (br == 0x7fffffff) br = 0;
+  const size_t src = (size_t)br * B + b;
+  for (int k = threadIdx.x; k < t_stride; k += blockDim.x) best_pi[(size_t)b * t_stride + k] = pi[src * t_stride + k];
+  for (int k = threadIdx.x; k < n; k += blockDim.x) best_serve[(size_t)b * n + k] = serve[src * n + k];
+  if (threadIdx.x == 0) { best_cost[b] = bc; best_rep[b] = br; }
+}
+
+}  // namespace agh
+
+using namespace agh;
+
+extern "C" const char* agh_last_error(void) { return g_err; }
+extern "C" int agh_version(void) { return 100; }
+extern "C" unsigned long long agh_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+extern "C" size_t agh_wblob_floats(void) { return W_TOTAL; }
+
+extern "C" int agh_fleet_task(const int64_t* loc, const int64_t* type, const float* departure, const float* demand_all,
+                              const float* tw_left_levels, int level, int fleet, const double* duration3,
+                              const double* next_duration3, int nd_is_f32, int B, int N, uint8_t* coord, float* demand,
+                              float* tw_left, double* tw_right, double* duration, void* stream) {
+  AGH_CHECK_ARG(loc && type && departure && demand_all && tw_left_levels && duration3 && next_duration3);
+  AGH_CHECK_ARG(coord && demand && tw_left && tw_right && duration);
+  AGH_CHECK_ARG(level >= 0 && level <= 4 && fleet >= 1 && fleet <= 10 && B >= 0 && N >= 1);
+  if (B == 0) return AGH_OK;
+  const size_t total = (size_t)B * (N + 1);
+  fleet_task_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      loc, type, departure, demand_all, tw_left_levels + (size_t)level * B * N, fleet, duration3[0], duration3[1],
+      duration3[2], next_duration3[0], next_duration3[1], next_duration3[2], nd_is_f32, B, N, coord, demand, tw_left,
+      tw_right, duration);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+extern "C" int agh_chain_tw_left(float* tw_left_levels, int level, const float* serve, int B, int N, void* stream) {
+  AGH_CHECK_ARG(tw_left_levels && serve && level >= 0 && level <= 4 && B >= 0 && N >= 1);
+  if (B == 0) return AGH_OK;
+  const size_t total = (size_t)B * N;
+  chain_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tw_left_levels + (size_t)(level + 1) * B * N,
+                                                                                 serve, B, N);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+extern "C" int agh_get_costs(const void* pi, int pi_elem_bytes, int T, const uint8_t* coord, const float* demand, const float* tw_left,
+                             const double* tw_right, const double* duration, const float* distance, int B, int N,
+                             float* cost, int32_t* status, void* stream) {
+  AGH_CHECK_ARG(pi && coord && demand && tw_left && tw_right && duration && distance && cost && status);
+  AGH_CHECK_ARG(B >= 0 && N >= 1 && T >= 1 && (pi_elem_bytes == 8 || pi_elem_bytes == 2));
+  if (B == 0) return AGH_OK;
+  const size_t threads = (size_t)B * 32;
+  const unsigned grid = (unsigned)((threads + 127) / 128);
+  if (pi_elem_bytes == 8)
+    get_costs_kernel<int64_t><<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int64_t*>(pi), T, coord, demand, tw_left,
+                                                                      tw_right, duration, distance, B, N, cost, status);
+  else
+    get_costs_kernel<int16_t><<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int16_t*>(pi), T, coord, demand, tw_left,
+                                                                      tw_right, duration, distance, B, N, cost, status);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+extern "C" int agh_state_get_mask(const agh_state* st, uint8_t* mask, void* stream) {
+  AGH_CHECK_ARG(st && mask && st->coord && st->demand && st->tw_left && st->tw_right && st->duration && st->distance);
+  AGH_CHECK_ARG(st->prev_a && st->used_capacity && st->visited && st->cur_free_time && st->B >= 0 && st->N >= 1);
+  if (st->B == 0) return AGH_OK;
+  state_mask_kernel<<<st->B, 128, 0, (cudaStream_t)stream>>>(*st, mask);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+extern "C" int agh_state_update(const agh_state* st, const int64_t* selected, void* stream) {
+  AGH_CHECK_ARG(st && selected && st->coord && st->demand && st->tw_left && st->duration && st->distance);
+  AGH_CHECK_ARG(st->prev_a && st->used_capacity && st->visited && st->lengths && st->cur_free_time && st->serve_time);
+  if (st->B == 0) return AGH_OK;
+  state_update_kernel<<<(st->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*st, selected);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+extern "C" int agh_best_of(const float* costs, const int16_t* pi, const float* serve, int R, int B, int N, int t_stride,
+                           float* best_cost, int16_t* best_pi, float* best_serve, int32_t* best_rep, void* stream) {
+  AGH_CHECK_ARG(costs && pi && serve && best_cost && best_pi && best_serve && best_rep && R >= 1 && B >= 0 && N >= 1);
+  if (B == 0) return AGH_OK;
+  best_of_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(costs, pi, serve, R, B, N + 1, t_stride, best_cost, best_pi, best_serve,
+                                                      best_rep);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}

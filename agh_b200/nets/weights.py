@@ -1,0 +1,53 @@
+"""Pack a reference-compatible state_dict into the f32 weight blob libagh_b200 consumes.
+
+Layout (floats) is declared in include/agh_b200.h and agh_b200/csrc/common.cuh.  Algebraic folds
+applied here, in f64, once per weight version:
+  * eval-mode BatchNorm1d (graph_encoder.py:135-138) -> per-channel scale/shift;
+  * project_out (attention_model.py:152,568) is absorbed into the logit keys:
+      logits_j = (W_out o) . LK_j / sqrt(128) = o . (W_out^T LK_j) / sqrt(128)
+    so the decoder projection for LK' is (W_out^T W_node[256:384] / sqrt(128));
+  * the node part of project_step_context (attention_model.py:149,432-433) becomes a per-node
+    table P_sc = h W_sc[:, :128]^T computed once per instance; the capacity and time columns stay
+    as two vectors; the 1/sqrt(16) glimpse scale (attention_model.py:559) is folded into K.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+D, H, FF, LAYERS = 128, 8, 512, 3
+BN_EPS = 1e-5
+
+
+def blob_floats() -> int:
+    layer = D * 3 * D + D * D + 2 * D + D * FF + FF + FF * D + D + 2 * D
+    return 92 * D + 3 * D + D + LAYERS * layer + D * 4 * D + D * D + 10 * D + 2 * D
+
+
+def pack_weights(sd: Dict[str, torch.Tensor], device=None) -> torch.Tensor:
+    g = lambda k: sd[k].detach().to(device=device, dtype=torch.float64)
+    parts = [g('loc_embedding.weight'), g('init_embed.weight').t(), g('init_embed.bias')]
+    for l in range(LAYERS):
+        pre = 'embedder.layers.%d.' % l
+        heads = lambda k: g(pre + '0.module.' + k).permute(1, 0, 2).reshape(D, D)       # [c][h*16+k]
+        parts.append(torch.cat((heads('W_query'), heads('W_key'), heads('W_val')), 1))   # [128][384]
+        parts.append(g(pre + '0.module.W_out').reshape(D, D))                            # [h*16+k][c]
+        s1 = g(pre + '1.normalizer.weight') / torch.sqrt(g(pre + '1.normalizer.running_var') + BN_EPS)
+        t1 = g(pre + '1.normalizer.bias') - g(pre + '1.normalizer.running_mean') * s1
+        parts += [s1, t1]
+        parts += [g(pre + '2.module.0.weight').t(), g(pre + '2.module.0.bias'),
+                  g(pre + '2.module.2.weight').t(), g(pre + '2.module.2.bias')]
+        s2 = g(pre + '3.normalizer.weight') / torch.sqrt(g(pre + '3.normalizer.running_var') + BN_EPS)
+        t2 = g(pre + '3.normalizer.bias') - g(pre + '3.normalizer.running_mean') * s2
+        parts += [s2, t2]
+    wn = g('project_node_embeddings.weight')                 # [384][128]
+    wout = g('project_out.weight')                           # [128][128]  glimpse = W_out o
+    wsc = g('project_step_context.weight')                   # [128][130]
+    lk_fold = (wout.t() @ wn[2 * D:3 * D]) / math.sqrt(D)    # [c][e]
+    wdec = torch.cat((wn[0:D].t() / math.sqrt(D // H), wn[D:2 * D].t(), lk_fold.t(), wsc[:, :D].t()), 1)   # [128][512]
+    parts += [wdec, g('project_fixed_context.weight').t(), g('fleets_embedding.weight'), wsc[:, D], wsc[:, D + 1]]
+    blob = torch.cat([p.contiguous().reshape(-1) for p in parts]).to(torch.float32).contiguous()
+    assert blob.numel() == blob_floats(), (blob.numel(), blob_floats())
+    return blob

@@ -1,0 +1,196 @@
+"""Thin host wrappers over the C ABI: allocate outputs with torch, pass raw pointers + stream.
+
+Nothing here computes; every function is one (or a fixed few) calls into libagh_b200.so on the
+current CUDA stream.  CPU tensors are rejected (agh_b200._lib.ptr raises): no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+
+D, KS = 128, _lib.KEY_STRIDE
+
+
+@dataclass
+class FleetTask:
+    """Node vectors of one fleet sub-problem in the layout the kernels read."""
+    coord: torch.Tensor      # [B,n] u8, coord[:,0] = 0 (depot)
+    demand: torch.Tensor     # [B,N] f32
+    tw_left: torch.Tensor    # [B,n] f32
+    tw_right: torch.Tensor   # [B,n] f64
+    duration: torch.Tensor   # [B,n] f64, duration[:,0] = 0
+    twr_f32: bool            # tw_right carried f32 values at the caller (fleet 10)
+    fleet: int               # 0..9, or -1 when fleet_ids is given
+    fleet_ids: Optional[torch.Tensor] = None   # [B] i32
+
+    @property
+    def B(self) -> int:
+        return self.coord.size(0)
+
+    @property
+    def N(self) -> int:
+        return self.demand.size(1)
+
+    @staticmethod
+    def from_input(inp: Dict[str, torch.Tensor]) -> 'FleetTask':
+        """Accept the reference's fleet-batch dict (train.py:53-57): loc i64 [B,N], demand f32 [B,N],
+        duration f64 [B,N], tw_right f64|f32 [B,n], tw_left f32 [B,n], fleet i64 [B,1].  'distance' is ignored:
+        the table is model state, not a per-instance stride-0 tensor."""
+        loc = inp['loc']
+        B, N = loc.shape
+        coord = torch.zeros(B, N + 1, dtype=torch.uint8, device=loc.device)
+        coord[:, 1:] = loc.to(torch.uint8)
+        duration = torch.zeros(B, N + 1, dtype=torch.float64, device=loc.device)
+        duration[:, 1:] = inp['duration'].to(torch.float64)
+        fl = inp['fleet'].reshape(-1)
+        # a batch normally holds one fleet; keep per-instance ids for generality without a host sync
+        return FleetTask(coord=coord, demand=inp['demand'].to(torch.float32).contiguous(),
+                         tw_left=inp['tw_left'].to(torch.float32).contiguous(),
+                         tw_right=inp['tw_right'].to(torch.float64).contiguous(), duration=duration,
+                         twr_f32=inp['tw_right'].dtype == torch.float32, fleet=-1,
+                         fleet_ids=fl.to(torch.int32).contiguous())
+
+
+def fleet_task(loc, type_, departure, demand_all, tw_left_levels, level: int, fleet: int, duration3, next_duration3,
+               nd_is_f32: bool) -> FleetTask:
+    """a1 fused (train.py:40-57): one launch builds every node vector of fleet `fleet` (1..10)."""
+    B, N = loc.shape
+    dev = loc.device
+    coord = torch.empty(B, N + 1, dtype=torch.uint8, device=dev)
+    demand = torch.empty(B, N, dtype=torch.float32, device=dev)
+    tw_left = torch.empty(B, N + 1, dtype=torch.float32, device=dev)
+    tw_right = torch.empty(B, N + 1, dtype=torch.float64, device=dev)
+    duration = torch.empty(B, N + 1, dtype=torch.float64, device=dev)
+    d3 = (C.c_double * 3)(*[float(x) for x in duration3])
+    nd3 = (C.c_double * 3)(*[float(x) for x in next_duration3])
+    check(lib().agh_fleet_task(ptr(loc, torch.int64), ptr(type_, torch.int64), ptr(departure, torch.float32),
+                               ptr(demand_all, torch.float32), ptr(tw_left_levels, torch.float32), level, fleet,
+                               C.cast(d3, C.c_void_p), C.cast(nd3, C.c_void_p), int(nd_is_f32), B, N, ptr(coord),
+                               ptr(demand), ptr(tw_left), ptr(tw_right), ptr(duration), stream_ptr(dev)))
+    return FleetTask(coord, demand, tw_left, tw_right, duration, bool(nd_is_f32), fleet - 1)
+
+
+def chain_tw_left(tw_left_levels, level: int, serve) -> None:
+    _, B, N = tw_left_levels.shape
+    check(lib().agh_chain_tw_left(ptr(tw_left_levels, torch.float32), level, ptr(serve, torch.float32), B, N,
+                                  stream_ptr(serve.device)))
+
+
+def init_embed(wblob, task: FleetTask) -> torch.Tensor:
+    B, N = task.B, task.N
+    h0 = torch.empty(B, N + 1, D, dtype=torch.float32, device=wblob.device)
+    check(lib().agh_init_embed(ptr(wblob, torch.float32), ptr(task.coord), ptr(task.demand), ptr(task.tw_left),
+                               ptr(task.tw_right), int(task.twr_f32), B, N, ptr(h0), stream_ptr(wblob.device)))
+    return h0
+
+
+def _workspace(B, N, dev):
+    nbytes = lib().agh_encoder_workspace_bytes(B, N)
+    return torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+
+
+def encode(wblob, task: FleetTask) -> torch.Tensor:
+    """a2+a3: init embedding + 3 encoder layers (eval-mode BatchNorm)."""
+    B, N = task.B, task.N
+    dev = wblob.device
+    h = torch.empty(B, N + 1, D, dtype=torch.float32, device=dev)
+    ws = _workspace(B, N, dev)
+    check(lib().agh_encode(ptr(wblob, torch.float32), ptr(task.coord), ptr(task.demand), ptr(task.tw_left),
+                           ptr(task.tw_right), int(task.twr_f32), B, N, ptr(h), ptr(ws), stream_ptr(dev)))
+    return h
+
+
+def encode_layers(wblob, h0) -> torch.Tensor:
+    B, n, _ = h0.shape
+    h = torch.empty_like(h0)
+    ws = _workspace(B, n - 1, h0.device)
+    check(lib().agh_encode_layers(ptr(wblob, torch.float32), ptr(h0, torch.float32), B, n - 1, ptr(h), ptr(ws),
+                                  stream_ptr(h0.device)))
+    return h
+
+
+def precompute(wblob, h, task: FleetTask):
+    """a4: keys [B,3,n,132], psc [B,n,128], qbase [B,128]."""
+    B, n, _ = h.shape
+    dev = h.device
+    keys = torch.empty(B, 3, n, KS, dtype=torch.float32, device=dev)
+    psc = torch.empty(B, n, D, dtype=torch.float32, device=dev)
+    qbase = torch.empty(B, D, dtype=torch.float32, device=dev)
+    check(lib().agh_precompute(ptr(wblob, torch.float32), ptr(h, torch.float32),
+                               ptr(task.fleet_ids, torch.int32) if task.fleet_ids is not None else None,
+                               max(task.fleet, 0), B, n - 1, ptr(keys), ptr(psc), ptr(qbase), stream_ptr(dev)))
+    return keys, psc, qbase
+
+
+def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.AGH_GREEDY, temp: float = 1.0,
+           seed: int = 0, id_offset: int = 0, actions: Optional[torch.Tensor] = None, replay_steps: int = 0,
+           reps: int = 1, inject_logp: Optional[torch.Tensor] = None, want_logp_sel: bool = False,
+           want_logp_full: bool = False, want_dumps: bool = False, t_stride: Optional[int] = None):
+    """a5-a12 + a14.  `reps` > 1 runs reps*B rollouts sharing the B key sets (sample_many)."""
+    Bk, N = task.B, task.N
+    n = N + 1
+    B = Bk * reps
+    dev = keys.device
+    T = max(2 * N - 1, 1) if t_stride is None else t_stride
+    out = {
+        'pi': torch.empty(B, T, dtype=torch.int16, device=dev),
+        'steps': torch.empty(B, dtype=torch.int32, device=dev),
+        'll': torch.empty(B, dtype=torch.float32, device=dev),
+        'cost': torch.empty(B, dtype=torch.float32, device=dev),
+        'serve': torch.empty(B, n, dtype=torch.float32, device=dev),
+    }
+    if want_logp_sel:
+        out['logp_sel'] = torch.empty(B, T, dtype=torch.float32, device=dev)
+    if want_logp_full:
+        out['logp_full'] = torch.zeros(B, T, n, dtype=torch.float32, device=dev)
+    if want_dumps:
+        out['mask_dump'] = torch.zeros(B, T, (n + 31) // 32, dtype=torch.int32, device=dev)
+        out['used_dump'] = torch.zeros(B, T, dtype=torch.float32, device=dev)
+        out['cft_dump'] = torch.zeros(B, T, dtype=torch.float64, device=dev)
+    if actions is not None:
+        assert actions.dtype == torch.int16 and actions.shape == (B, T), (actions.dtype, actions.shape, (B, T))
+    a = _lib.DecodeArgs(
+        keys=ptr(keys, torch.float32), psc=ptr(psc, torch.float32), qbase=ptr(qbase, torch.float32),
+        coord=ptr(task.coord, torch.uint8), demand=ptr(task.demand, torch.float32),
+        tw_left=ptr(task.tw_left, torch.float32), tw_right=ptr(task.tw_right, torch.float64),
+        duration=ptr(task.duration, torch.float64), distance=ptr(distance, torch.float32),
+        wblob=ptr(wblob, torch.float32), key_mod=Bk if reps > 1 else 0, mode=mode, temp=float(temp),
+        seed=int(seed) & (2 ** 64 - 1), id_offset=int(id_offset), actions=ptr(actions), replay_steps=int(replay_steps),
+        inject_logp=ptr(inject_logp), t_stride=T, pi=ptr(out['pi']), steps=ptr(out['steps']), ll=ptr(out['ll']),
+        cost=ptr(out['cost']), serve=ptr(out['serve']), logp_sel=ptr(out.get('logp_sel')),
+        logp_full=ptr(out.get('logp_full')), mask_dump=ptr(out.get('mask_dump')), used_dump=ptr(out.get('used_dump')),
+        cft_dump=ptr(out.get('cft_dump')), B=B, N=N)
+    check(lib().agh_decode(C.byref(a), stream_ptr(dev)))
+    return out
+
+
+def get_costs(pi, task: FleetTask, distance):
+    """a13: returns (cost [B] f32, status [B] i32)."""
+    B, T = pi.shape
+    dev = pi.device
+    cost = torch.empty(B, dtype=torch.float32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    assert pi.dtype in (torch.int64, torch.int16)
+    check(lib().agh_get_costs(ptr(pi), pi.element_size(), T, ptr(task.coord), ptr(task.demand), ptr(task.tw_left),
+                              ptr(task.tw_right), ptr(task.duration), ptr(distance, torch.float32), B, task.N,
+                              ptr(cost), ptr(status), stream_ptr(dev)))
+    return cost, status
+
+
+def best_of(costs, pi, serve, R: int, B: int):
+    """a16: first-minimum replica per instance (utils/functions.py:216-219)."""
+    dev = costs.device
+    T, n = pi.size(1), serve.size(1)
+    bc = torch.empty(B, dtype=torch.float32, device=dev)
+    bp = torch.empty(B, T, dtype=torch.int16, device=dev)
+    bs = torch.empty(B, n, dtype=torch.float32, device=dev)
+    br = torch.empty(B, dtype=torch.int32, device=dev)
+    check(lib().agh_best_of(ptr(costs, torch.float32), ptr(pi, torch.int16), ptr(serve, torch.float32), R, B, n - 1, T,
+                            ptr(bc), ptr(bp), ptr(bs), ptr(br), stream_ptr(dev)))
+    return bc, bp, bs, br

@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Headline benchmark: AGH-100 greedy rollout throughput (BASELINE.json metric, config C3).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU port (oracle)
+
+One "step" = one greedy rollout (all 10 fleets: assemble -> encode -> precompute -> fused decode ->
+cost) of one batch of `--batch` (default 10,000) synthetic AGH-100 instances per GPU.  Weak scaling:
+every rank owns its own batch; no data-path collective.  Prints ONE JSON line (rank 0).
+
+  value    : instances/s with the instance arrays already resident in HBM (CUDA-event timed,
+             barrier + synchronize on both sides, max over ranks);
+  e2e      : the same metric through the public API train.rollout(model, dataset, opts) with pinned
+             HOST arrays: H2D of the batch and D2H of the [B,10] cost table inside the timed region;
+  roofline : the fused decode kernel against the measured HBM copy bandwidth, with
+             A_step(N) = 1573 (N+1) + 1600 algorithmic bytes per instance-step;
+  cpu_baseline : the oracle port (same algorithm in PyTorch-CPU ops, all host threads) on a bounded
+             sample of the same workload, rank 0, N=1 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = 'agh100_greedy_rollout_instances_per_sec'
+UNIT = 'instances/s'
+
+
+def a_step_bytes(N):
+    return 1573 * (N + 1) + 1600
+
+
+def f_enc_flops(N):
+    return 1278720 * (N + 1) + 1536 * (N + 1) ** 2 + 32768
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1590.0))), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_batch(B, N, seed):
+    from agh_b200.problems.agh.problem_agh import generate_arrays
+    np.random.seed(seed)
+    return generate_arrays(B, N)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference algorithm on the host cores (oracle port; the Python reference
+    itself cannot travel to the GPU box).  Each step = one rollout of a bounded sample."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    from oracle import agh_oracle as O
+    tb, W = O.Tables.load(), O.random_init_weights(1234)
+    B = args.cpu_sample
+    inst = make_batch(B, args.flights, 4321)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        costs = O.rollout(W, tb, inst)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    val = B / (ms / 1e3)
+    sample = '%d of the same seed-4321 AGH-%d instances per step, all 10 fleets, greedy' % (B, args.flights)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'AGH-%d greedy rollout, 10 fleets, random-init seed-1234 weights' % args.flights,
+                       'flights': args.flights, 'sample_batch': B},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'avg_cost': float(costs.sum(1).mean())}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch.distributed as dist
+    from agh_b200 import AttentionModel, AGH, AGHDataset, ops, _lib
+    from agh_b200.train import rollout
+    rank = int(os.environ.get('RANK', 0))
+    ws = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU port'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if ws > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    N, B = args.flights, args.batch
+    torch.manual_seed(1234)
+    model = AttentionModel(128, 128, AGH).to(dev)
+    model.eval()
+    model.set_decode_type('greedy')
+    host = make_batch(B, N, 4321 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    ds = AGHDataset.__new__(AGHDataset)
+    torch.utils.data.Dataset.__init__(ds)
+    ds.arrays, ds.size = host, B
+    resident = {k: v.to(dev) for k, v in host.items()}
+    info = model.fleet_info
+    blob, dist_tab = model.weight_blob(), model.distance_table()
+    lib = _lib.lib()
+    n = N + 1
+
+    # ---- device-resident step with per-phase CUDA events (the decode kernel is the roofline kernel)
+    def step_resident(events=None):
+        loc, type_ = resident['loc'], resident['type']
+        lv = resident['arrival'].repeat(6, 1, 1).contiguous()
+        costs, inst_steps = [], []
+        for f in info['order']:
+            p = info['precedence'][f]
+            nd = info['next_duration'][p]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if events is not None else None
+            task = ops.fleet_task(loc, type_, resident['departure'], resident['demand'], lv, p, f, info['duration'][f], nd,
+                                  nd_is_f32=all(type(v) is float for v in nd))
+            if ev: ev[0].record()
+            h = ops.encode(blob, task)
+            if ev: ev[1].record()
+            keys, psc, qbase = ops.precompute(blob, h, task)
+            if ev: ev[2].record()
+            out = ops.decode(blob, dist_tab, task, keys, psc, qbase, mode=_lib.AGH_GREEDY)
+            if ev: ev[3].record()
+            _, status = ops.get_costs(out['pi'], task, dist_tab)
+            ops.chain_tw_left(lv, p, out['serve'])
+            costs.append(out['cost'])
+            inst_steps.append(out['steps'].sum())
+            if ev: events.append(ev)
+        return torch.stack(costs, 1), torch.stack(inst_steps), status
+
+    opts = types.SimpleNamespace(eval_batch_size=B, device=dev, no_progress_bar=True)
+
+    for _ in range(args.warmup):
+        step_resident()
+        rollout(model, ds, opts)
+
+    # ---- timed: device-resident
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.agh_launch_count()
+    events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        costs, inst_steps, status = step_resident(events)
+    e1.record()
+    barrier()
+    ms_res = e0.elapsed_time(e1) / args.steps
+    launches = (lib.agh_launch_count() - launches0) // args.steps
+    assert int(status.max()) == 0, 'invalid tours'
+    t_enc = sum(ev[0].elapsed_time(ev[1]) for ev in events) / args.steps
+    t_pre = sum(ev[1].elapsed_time(ev[2]) for ev in events) / args.steps
+    t_dec = sum(ev[2].elapsed_time(ev[3]) for ev in events) / args.steps
+    total_inst_steps = float(inst_steps.sum().item())              # instance-steps per step (10 decode launches)
+
+    # ---- timed: end to end through the public API, pinned host inputs
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        host_costs = rollout(model, ds, opts)                       # H2D batch, 10 fleets, D2H [B,10]
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_res, ms_e2e, t_enc, t_pre, t_dec], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_res, ms_e2e, t_enc, t_pre, t_dec = t.tolist()
+
+    if rank == 0:
+        hbm, tflops, which = peaks()
+        dec_launch_ms = t_dec / 10.0
+        inst_steps_per_launch = total_inst_steps / 10.0
+        achieved = a_step_bytes(N) * inst_steps_per_launch / (dec_launch_ms * 1e-3) / 1e9
+        enc_tflops = f_enc_flops(N) * B * 10 / ((t_enc + t_pre) * 1e-3) / 1e12
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        line = {
+            'metric': METRIC, 'value': B * ws / (ms_res * 1e-3), 'unit': UNIT, 'n_gpus': ws, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'AGH-%d greedy rollout, batch %d per GPU, all 10 fleets per instance (configs[2])' % (N, B),
+                       'flights': N, 'per_gpu_batch': B, 'weights': 'random-init torch.manual_seed(1234)',
+                       'instances': 'generate_agh_data semantics, np seed 4321+rank',
+                       'l2': 'inputs larger than L2 (keys %.2f GB per fleet launch vs 126 MB L2)' % (B * 3 * n * 528 / 1e9),
+                       'parallelism': 'instances sharded, %d rank(s), no data-path collective' % ws},
+            'clocks': clocks,
+            'e2e': {'value': B * ws / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': B * 10 * 4,
+                    'ms_per_step': ms_e2e, 'api': 'agh_b200.train.rollout(model, dataset, opts)'},
+            'gpu_launches': int(launches),
+            'roofline': {'kernel': 'decode_kernel (agh_decode)', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm,
+                         'unit': 'GB/s', 'frac': achieved / hbm, 'traffic': None, 'peak_source': which,
+                         'algorithmic_bytes_per_instance_step': a_step_bytes(N),
+                         'instance_steps_per_launch': inst_steps_per_launch, 'launch_ms': dec_launch_ms,
+                         'share_of_step': t_dec / ms_res,
+                         'note': 'keys stay in shared memory across steps, so the effective fraction may exceed 1; '
+                                 'physical DRAM bytes are in profiles/'},
+            'roofline_encoder': {'kernels': 'sgemm_kernel + mha_kernel + init_embed (agh_encode, agh_precompute)',
+                                 'bound': 'tensor', 'achieved': enc_tflops, 'peak': tflops, 'unit': 'TFLOP/s',
+                                 'frac': enc_tflops / tflops, 'share_of_step': (t_enc + t_pre) / ms_res,
+                                 'note': 'fp32 CUDA-core path this round; peak is the measured bf16 cuBLAS figure'},
+            'phase_ms': {'encode': t_enc, 'precompute': t_pre, 'decode': t_dec},
+            'decode_instance_steps_per_sec': total_inst_steps * ws / (ms_res * 1e-3),
+            'avg_cost': float(host_costs.sum(1).mean()),
+        }
+        if ws == 1 and not args.no_cpu_baseline:
+            from oracle import agh_oracle as O
+            tb, W = O.Tables.load(), O.random_init_weights(1234)
+            Bc = args.cpu_baseline_sample
+            sub = {k: v[:Bc].clone() for k, v in host.items()}
+            t0 = time.perf_counter()
+            ref = O.rollout(W, tb, sub)
+            dt = time.perf_counter() - t0
+            line['cpu_baseline'] = {'value': Bc / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                                    'sample': 'first %d instances of the same batch, all 10 fleets, %.1f s' % (Bc, dt),
+                                    'avg_cost_same_instances': {'cpu': float(ref.sum(1).mean()),
+                                                                'gpu': float(host_costs[:Bc].sum(1).mean())}}
+        print(json.dumps(line))
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
+    ap.add_argument('--flights', type=int, default=100)
+    ap.add_argument('--batch', type=int, default=10000, help='instances per GPU per step')
+    ap.add_argument('--cpu-sample', type=int, default=128, help='--impl reference: instances per step')
+    ap.add_argument('--cpu-baseline-sample', type=int, default=256)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_cuda(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -47,6 +47,8 @@ enum { AGH_TOUR_INVALID = 1, AGH_CAPACITY_EXCEEDED = 2, AGH_TW_VIOLATED = 4 };
 
 const char* agh_last_error(void);
 int agh_version(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches) */
+unsigned long long agh_launch_count(void);
 
 /* ---- packed weights -------------------------------------------------------------------------
  * One f32 blob built by the host from the reference state_dict (agh_b200/nets/weights.py);
@@ -79,12 +81,17 @@ int agh_chain_tw_left(float* tw_left_levels, int level, const float* serve /*[B]
  *   h_out[B][n][128] f32.  workspace: agh_encoder_workspace_bytes(B,N) bytes.
  */
 size_t agh_encoder_workspace_bytes(int B, int N);
+/* twr_f32: tw_right held f32 values in the caller (fleet 10) -> tw_right/1440 is an f32 division */
 int agh_encode(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
-               const double* tw_right, int B, int N, float* h_out, void* workspace, void* stream);
+               const double* tw_right, int twr_f32, int B, int N, float* h_out, void* workspace, void* stream);
 
 /* init embedding only (attention_model.py:272-294): h0[B][n][128] */
 int agh_init_embed(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
-                   const double* tw_right, int B, int N, float* h0, void* stream);
+                   const double* tw_right, int twr_f32, int B, int N, float* h0, void* stream);
+
+/* encoder layers only (graph_encoder.py:195-207) on caller-provided initial embeddings h0[B][n][128];
+ * h0 may alias neither h_out nor the workspace. */
+int agh_encode_layers(const float* wblob, const float* h0, int B, int N, float* h_out, void* workspace, void* stream);
 
 /* ---- a4: decoder precompute (attention_model.py:392-414,604-611) ---------------------------
  *   h[B][n][128] -> keys[B][3][n][132] (K'/4, V, LK'), psc[B][n][128], qbase[B][128]
@@ -135,9 +142,9 @@ typedef struct {
 int agh_decode(const agh_decode_args* args, void* stream);
 
 /* ---- a13: tour validation + cost (problem_agh.py:18-66) ------------------------------------
- *   pi[B][T] i64.  cost[B] f32, status[B] i32 (0 = valid; AGH_TOUR_INVALID | ... otherwise).
+ *   pi[B][T] i64 or i16.  cost[B] f32, status[B] i32 (0 = valid; AGH_TOUR_INVALID | ... otherwise).
  */
-int agh_get_costs(const int64_t* pi, int T, const uint8_t* coord, const float* demand, const float* tw_left,
+int agh_get_costs(const void* pi, int pi_elem_bytes /* 8: int64 (reference dtype), 2: int16 (agh_decode output) */, int T, const uint8_t* coord, const float* demand, const float* tw_left,
                   const double* tw_right, const double* duration, const float* distance, int B, int N,
                   float* cost, int32_t* status, void* stream);
 

