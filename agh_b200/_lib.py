@@ -75,6 +75,8 @@ SYMBOLS = {
     'agh_version': (_I, []),
     'agh_launch_count': (C.c_ulonglong, []),
     'agh_wblob_floats': (C.c_size_t, []),
+    'agh_sizeof_decode_args': (C.c_size_t, []),
+    'agh_sizeof_state': (C.c_size_t, []),
     'agh_fleet_task': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     'agh_chain_tw_left': (_I, [_P, _I, _P, _I, _I, _P]),
     'agh_encoder_workspace_bytes': (C.c_size_t, [_I, _I]),

@@ -201,6 +201,8 @@ extern "C" const char* agh_last_error(void) { return g_err; }
 extern "C" int agh_version(void) { return 100; }
 extern "C" unsigned long long agh_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" size_t agh_wblob_floats(void) { return W_TOTAL; }
+extern "C" size_t agh_sizeof_decode_args(void) { return sizeof(agh_decode_args); }
+extern "C" size_t agh_sizeof_state(void) { return sizeof(agh_state); }
 
 extern "C" int agh_fleet_task(const int64_t* loc, const int64_t* type, const float* departure, const float* demand_all,
                               const float* tw_left_levels, int level, int fleet, const double* duration3,

@@ -140,6 +140,8 @@ typedef struct {
 } agh_decode_args;
 
 int agh_decode(const agh_decode_args* args, void* stream);
+/* ABI guard for FFI bindings: sizeof(agh_decode_args) as compiled */
+size_t agh_sizeof_decode_args(void);
 
 /* ---- a13: tour validation + cost (problem_agh.py:18-66) ------------------------------------
  *   pi[B][T] i64 or i16.  cost[B] f32, status[B] i32 (0 = valid; AGH_TOUR_INVALID | ... otherwise).
@@ -161,6 +163,7 @@ typedef struct {
   int B, N;
 } agh_state;
 
+size_t agh_sizeof_state(void);
 int agh_state_get_mask(const agh_state* st, uint8_t* mask /*[B][n], 1 = infeasible*/, void* stream);
 int agh_state_update(const agh_state* st, const int64_t* selected /*[B]*/, void* stream);
 
