@@ -157,3 +157,45 @@ def test_get_costs_rejects_bad_tours(weights, tables):
     one = torch.arange(1, 21).repeat(4, 1)
     with pytest.raises(AssertionError):
         O.get_costs(task, one)
+
+
+def test_c_env_matches_golden(tables):
+    """oracle/agh_env.c (scalar C) against the reference's nearest-neighbour KAT and the torch oracle's masks."""
+    import ctypes as C
+    import os
+    import subprocess
+    from conftest import ROOT
+    subprocess.run(['make', '-C', os.path.join(ROOT, 'oracle'), '-s'], check=True)
+    lib = C.CDLL(os.path.join(ROOT, 'oracle', '_build', 'libagh_env.so'))
+    g = load_golden('kat_agh20.npz')
+    inst = make_instances(20)
+    B, N = inst['loc'].shape
+    lv = O.new_tw_left_levels(inst)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    costs = []
+    for k, f in enumerate(tables.order):
+        task = O.fleet_task(tables, inst, f, lv)
+        loc, dem, twl = task['loc'].contiguous(), task['demand'].contiguous(), task['tw_left'].contiguous()
+        twr, dur, dist = task['tw_right'].double().contiguous(), task['duration'].contiguous(), tables.distance.contiguous()
+        pi = torch.zeros(B, 2 * N, dtype=torch.int64)
+        steps = torch.zeros(B, dtype=torch.int32)
+        serve = torch.zeros(B, N + 1)
+        cost = torch.zeros(B)
+        masks = torch.zeros(B, 2 * N, N + 1, dtype=torch.uint8) if k in (0, 9) else None
+        lib.agh_c_nearest_neighbor(B, N, P(loc), P(dem), P(twl), P(twr), P(dur), P(dist), P(pi), P(steps), P(serve), P(cost),
+                                   P(masks) if masks is not None else None)
+        ref_cost, ref_serve, ref_pi = O.nearest_neighbor(task)
+        T = ref_pi.size(1)
+        assert torch.equal(pi[:, :T], ref_pi) and int(steps.max()) == T
+        assert torch.equal(serve, ref_serve)
+        assert np.allclose(cost.numpy(), g['nearest_neighbor_costs'][:, k], rtol=1e-6, atol=0)
+        if masks is not None:       # masks of the torch oracle along the same tours
+            env = O.Env(task)
+            for t in range(T):
+                alive = steps > t
+                assert torch.equal(masks[alive, t].bool(), env.mask()[alive])
+                env.update(ref_pi[:, t])
+        costs.append(cost)
+        O.chain_tw_left(tables, lv, f, serve)
+    avg = torch.stack(costs, 1).sum(1).mean().item()
+    assert abs(avg - 147099.953125) / 147099.953125 < 1e-6
