@@ -22,7 +22,7 @@ NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,c
 
 AGH_GREEDY, AGH_SAMPLING, AGH_REPLAY = 0, 1, 2
 AGH_TOUR_INVALID, AGH_CAPACITY_EXCEEDED, AGH_TW_VIOLATED = 1, 2, 4
-KEY_STRIDE = 132
+KEY_STRIDE = 128
 D = 128
 
 
@@ -51,7 +51,7 @@ class DecodeArgs(C.Structure):
         ('keys', C.c_void_p), ('psc', C.c_void_p), ('qbase', C.c_void_p), ('coord', C.c_void_p),
         ('demand', C.c_void_p), ('tw_left', C.c_void_p), ('tw_right', C.c_void_p), ('duration', C.c_void_p),
         ('distance', C.c_void_p), ('wblob', C.c_void_p),
-        ('key_mod', C.c_int), ('mode', C.c_int), ('temp', C.c_float), ('seed', C.c_uint64), ('id_offset', C.c_int64),
+        ('key_mod', C.c_int), ('smem_mats', C.c_int), ('mode', C.c_int), ('temp', C.c_float), ('seed', C.c_uint64), ('id_offset', C.c_int64),
         ('actions', C.c_void_p), ('replay_steps', C.c_int), ('inject_logp', C.c_void_p), ('t_stride', C.c_int),
         ('pi', C.c_void_p), ('steps', C.c_void_p), ('ll', C.c_void_p), ('cost', C.c_void_p), ('serve', C.c_void_p),
         ('logp_sel', C.c_void_p), ('logp_full', C.c_void_p), ('mask_dump', C.c_void_p), ('used_dump', C.c_void_p),

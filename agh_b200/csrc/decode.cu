@@ -7,10 +7,12 @@
 // fly so the [B,T,n] log-prob tensor is never materialised.
 //
 // Data layout:
-//   * the instance's K'/V/LK' rows ([n][132] f32 each, written by agh_precompute) are staged ONCE
-//     into shared memory with cp.async.bulk (TMA bulk copy, mbarrier completion) and stay there
-//     for all T steps; P_sc = W_sc[:, :128] h (the node part of the step-context projection) is
-//     staged too when it fits.  For N >= 200 the matrices that do not fit are read through L2.
+//   * the instance's K' rows are loaded ONCE into registers (16 NPL per thread) and its V / LK' rows
+//     ([n][128] f32, chunk-swizzled, written by agh_precompute) are staged ONCE into shared memory with
+//     cp.async.bulk (TMA bulk copy, mbarrier completion); all stay on chip for all T steps.
+//     P_sc = W_sc[:, :128] h (the node part of the step-context projection) is staged too when that
+//     does not cost a resident CTA.  At N = 100 this is 111 KB + 64 registers per instance, so TWO
+//     instances share an SM and hide each other's step latency; N = 300 streams V through L2.
 //   * W_out is folded into LK' (LK' = W_out^T W_lk / sqrt(128)), so a step is
 //       q = qbase + P_sc[prev] + w_cap (1-used) + w_time (cft/1440)
 //       s_hj = q_h . K'_jh ; a_h = softmax_j(s_h | mask) ; o_h = sum_j a_hj V_jh
@@ -84,42 +86,56 @@ __device__ __forceinline__ uint32_t pick_word(const uint32_t (&w)[NPL], int idx)
   return r;
 }
 
+// Residency of the per-instance matrices.  K' always lives in REGISTERS (lane l of warp h holds the 16
+// features of head h for its nodes l, l+32, ...: 16*NPL registers, the exact operand layout of the
+// compatibility dot products).  V / LK' / P_sc live in shared memory when the bit is set, else they are
+// read through L2 every step.
+enum { RES_V = 1, RES_L = 2, RES_P = 4 };
+
 struct DecodeSmem {
   // byte offsets into dynamic shared memory
-  size_t K, V, L, P, twr, dur, twl, dem, crd, dcur, z, serve, o, qb, wc, wt, red, bar, total;
+  size_t V, L, P, twr, dur, twl, dem, crd, dcur, z, serve, o, qb, wc, wt, red, mw, bar, total;
 };
 
-__host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int nsm) {
+__host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int res) {
   DecodeSmem s;
   const size_t npad = (size_t)npl * 32;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
-  s.K = take(nsm >= 1 ? (size_t)n * KS * 4 : 0);
-  s.V = take(nsm >= 2 ? (size_t)n * KS * 4 : 0);
-  s.L = take(nsm >= 3 ? (size_t)n * KS * 4 : 0);
-  s.P = take(nsm >= 4 ? (size_t)n * D * 4 : 0);
+  s.V = take((res & RES_V) ? (size_t)n * KS * 4 : 0);
+  s.L = take((res & RES_L) ? (size_t)n * KS * 4 : 0);
+  s.P = take((res & RES_P) ? (size_t)n * D * 4 : 0);
   s.twr = take(npad * 8); s.dur = take(npad * 8);
   s.twl = take(npad * 4); s.dem = take(npad * 4); s.crd = take(npad * 4);
   s.dcur = take(2 * npad * 4); s.z = take(npad * 4); s.serve = take(npad * 4);
   s.o = take(D * 4); s.qb = take(D * 4); s.wc = take(D * 4); s.wt = take(D * 4);
   s.red = take(8 * 8 * 4);
+  s.mw = take(16 * 4);
   s.bar = take(16);
   s.total = off;
   return s;
 }
 
-// NPL: nodes per lane in the glimpse (ceil(n/32)); NSM: how many of {K',V,LK',P_sc} live in smem.
-template <int NPL, int NSM>
-__global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) decode_kernel(const agh_decode_args a) {
+// Key rows are stored unpadded ([n][128] f32) with the 16-byte chunks of every aligned 8-chunk group
+// XOR-swizzled by (node & 7): lanes that read the same logical chunk of 8 consecutive nodes hit 8
+// different bank groups, so every LDS.128 below is conflict-free without padding bytes.
+__device__ __forceinline__ int swz(int chunk, int node) { return (chunk & ~7) | ((chunk ^ node) & 7); }
+
+// resident CTAs per SM the register budget is compiled for (65536 / (256 * regs))
+constexpr int decode_min_blocks(int npl) { return npl == 1 ? 3 : (npl <= 4 ? 2 : 1); }
+
+// NPL: nodes per lane in the glimpse (ceil(n/32)); RES: which of {V, LK', P_sc} live in smem.
+template <int NPL, int RES>
+__global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(const agh_decode_args a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int n = a.N + 1;
   const int b = blockIdx.x;
   const int kb = a.key_mod > 0 ? b % a.key_mod : b;      // source of keys / node vectors
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const DecodeSmem L = decode_smem_layout(n, NPL, NSM);
+  const DecodeSmem L = decode_smem_layout(n, NPL, RES);
   constexpr int NPAD = NPL * 32;
+  constexpr int MPT = (NPAD + 255) / 256;                 // mask nodes per thread (node = tid + 256 k)
 
-  float* sK = reinterpret_cast<float*>(smem + L.K);
   float* sV = reinterpret_cast<float*>(smem + L.V);
   float* sL = reinterpret_cast<float*>(smem + L.L);
   float* sP = reinterpret_cast<float*>(smem + L.P);
@@ -136,6 +152,7 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
   float* s_wc = reinterpret_cast<float*>(smem + L.wc);
   float* s_wt = reinterpret_cast<float*>(smem + L.wt);
   float* s_red = reinterpret_cast<float*>(smem + L.red);
+  uint32_t* s_mw = reinterpret_cast<uint32_t*>(smem + L.mw);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
   const float* gkeys = a.keys + (size_t)kb * 3 * n * KS;
@@ -150,15 +167,25 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
   if (tid == 0) {
     const uint32_t mat_bytes = (uint32_t)n * KS * 4;
     uint32_t total = 0;
-    if (NSM >= 1) total += mat_bytes;
-    if (NSM >= 2) total += mat_bytes;
-    if (NSM >= 3) total += mat_bytes;
-    if (NSM >= 4) total += (uint32_t)n * D * 4;
+    if (RES & RES_V) total += mat_bytes;
+    if (RES & RES_L) total += mat_bytes;
+    if (RES & RES_P) total += (uint32_t)n * D * 4;
     mbar_expect_tx(bar, total);
-    if (NSM >= 1) bulk_g2s(sK, gkeys, mat_bytes, bar);
-    if (NSM >= 2) bulk_g2s(sV, gkeys + (size_t)n * KS, mat_bytes, bar);
-    if (NSM >= 3) bulk_g2s(sL, gkeys + (size_t)2 * n * KS, mat_bytes, bar);
-    if (NSM >= 4) bulk_g2s(sP, gpsc, (uint32_t)n * D * 4, bar);
+    if (RES & RES_V) bulk_g2s(sV, gkeys + (size_t)n * KS, mat_bytes, bar);
+    if (RES & RES_L) bulk_g2s(sL, gkeys + (size_t)2 * n * KS, mat_bytes, bar);
+    if (RES & RES_P) bulk_g2s(sP, gpsc, (uint32_t)n * D * 4, bar);
+  }
+  // K' -> registers: the 16 features of head `warp` for nodes lane + 32 p (one-time global read)
+  float kreg[NPL][HD];
+#pragma unroll
+  for (int p = 0; p < NPL; ++p) {
+    const int j = lane + 32 * p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < n) v = __ldg(reinterpret_cast<const float4*>(gkeys + (size_t)j * KS) + swz(warp * 4 + i, j));
+      kreg[p][4 * i] = v.x; kreg[p][4 * i + 1] = v.y; kreg[p][4 * i + 2] = v.z; kreg[p][4 * i + 3] = v.w;
+    }
   }
   // node vectors and per-instance constants with ordinary loads while the bulk copies fly
   for (int j = tid; j < NPAD; j += 256) {
@@ -178,101 +205,113 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
   __syncthreads();
   mbar_wait(bar, 0);
 
-  const float* Km = NSM >= 1 ? sK : gkeys;
-  const float* Vm = NSM >= 2 ? sV : gkeys + (size_t)n * KS;
-  const float* Lm = NSM >= 3 ? sL : gkeys + (size_t)2 * n * KS;
-  const float* Pm = NSM >= 4 ? sP : gpsc;
+  const float* Vm = (RES & RES_V) ? sV : gkeys + (size_t)n * KS;
+  const float* Lm = (RES & RES_L) ? sL : gkeys + (size_t)2 * n * KS;
+  const float* Pm = (RES & RES_P) ? sP : gpsc;
 
-  // ---- per-lane node constants (nodes lane + 32p) ----
-  int cj[NPL];
-  float demj[NPL], twlj[NPL];
-  double twrj[NPL], durj[NPL];
+  // ---- constants of the node(s) whose feasibility this thread evaluates (node = tid + 256 k) ----
+  int cjm[MPT];
+  float demm[MPT], twlm[MPT];
+  double twrm[MPT], durm[MPT];
+  bool vis[MPT];
 #pragma unroll
-  for (int p = 0; p < NPL; ++p) {
-    const int j = lane + 32 * p;
-    cj[p] = s_crd[j]; demj[p] = s_dem[j]; twlj[p] = s_twl[j]; twrj[p] = s_twr[j]; durj[p] = s_dur[j];
+  for (int k = 0; k < MPT; ++k) {
+    const int j = tid + 256 * k;
+    const bool ok = j < NPAD;
+    cjm[k] = ok ? s_crd[j] : 0; demm[k] = ok ? s_dem[j] : 0.f; twlm[k] = ok ? s_twl[j] : 0.f;
+    twrm[k] = ok ? s_twr[j] : 0.0; durm[k] = ok ? s_dur[j] : 0.0;
+    vis[k] = false;
   }
 
   // ---- state (replicated in every thread) : state_agh.py:60-93 ----
   int prev = 0, t = 0, nvis = 0;
+  bool depot_seen = false;
   float used = 0.f, len = 0.f, ll = 0.f;
   double cft = -60.0;
-  uint32_t vw[NPL];
-#pragma unroll
-  for (int p = 0; p < NPL; ++p) vw[p] = 0u;
 
   const int h = warp;
   const bool replay = a.mode == AGH_REPLAY;
   const uint64_t rng_id = (uint64_t)(a.id_offset + b);
   const size_t trow = (size_t)b * a.t_stride;
   const int nwords = (n + 31) / 32;
+  const bool unit_temp = a.temp == 1.0f;
+  // 10 tanh(.) / temp <= shift: a fixed log-sum-exp shift needs no cross-warp max (exp(-2 shift) must stay
+  // normal, hence temp >= 0.25); colder temperatures take the exact max-merging path
+  const bool fixed_shift = a.temp >= 0.25f;
+  const float shift = __fdiv_rn(10.0f, a.temp);
 
   while (replay ? (t < a.replay_steps) : (nvis < n)) {
     const int cprev = s_crd[prev];
-    // (1) distance row of the current location, gathered by the coordinate of my nodes
-    float dd[NPL];
+    float* dc = s_dcur + (t & 1) * NPAD;
+    // (1) distance from the current location to the node(s) this thread masks
+    float ddm[MPT];
 #pragma unroll
-    for (int p = 0; p < NPL; ++p) dd[p] = (lane + 32 * p < n) ? __ldg(a.distance + NODE_SIZE * cprev + cj[p]) : 0.f;
+    for (int k = 0; k < MPT; ++k) ddm[k] = (tid + 256 * k < n) ? __ldg(a.distance + NODE_SIZE * cprev + cjm[k]) : 0.f;
 
     // (2) query for my head: attention_model.py:432-435,510-522
     const float rem = 1.0f - used;
-    const float tf = (float)(cft / 1440.0);
-    float q[HD];
+    float tf;
+    {   // (float)(cft / 1440.0) with an FMA-corrected reciprocal instead of the f64 division subroutine
+      const double inv = 1.0 / 1440.0;
+      const double q0 = cft * inv;
+      tf = (float)fma(fma(-q0, 1440.0, cft), inv, q0);
+    }
+    // (3) compatibilities of my nodes with head h against the register-resident K' (which already holds
+    //     the 1/sqrt(16)); q is consumed chunk by chunk and never kept
+    float s[NPL];
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) s[p] = 0.f;
     {
       const float4* pr = reinterpret_cast<const float4*>(Pm + (size_t)prev * D + h * HD);
       const float4* qb4 = reinterpret_cast<const float4*>(s_qb + h * HD);
       const float4* wc4 = reinterpret_cast<const float4*>(s_wc + h * HD);
       const float4* wt4 = reinterpret_cast<const float4*>(s_wt + h * HD);
+      float4 pv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = (RES & RES_P) ? pr[i] : __ldg(pr + i);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 pv = pr[i], bv = qb4[i], cv = wc4[i], tv = wt4[i];
-        q[4 * i + 0] = fmaf(tv.x, tf, fmaf(cv.x, rem, bv.x + pv.x));
-        q[4 * i + 1] = fmaf(tv.y, tf, fmaf(cv.y, rem, bv.y + pv.y));
-        q[4 * i + 2] = fmaf(tv.z, tf, fmaf(cv.z, rem, bv.z + pv.z));
-        q[4 * i + 3] = fmaf(tv.w, tf, fmaf(cv.w, rem, bv.w + pv.w));
+        const float4 bv = qb4[i], cv = wc4[i], tv = wt4[i];
+        float4 qv;
+        qv.x = fmaf(tv.x, tf, fmaf(cv.x, rem, bv.x + pv[i].x));
+        qv.y = fmaf(tv.y, tf, fmaf(cv.y, rem, bv.y + pv[i].y));
+        qv.z = fmaf(tv.z, tf, fmaf(cv.z, rem, bv.z + pv[i].z));
+        qv.w = fmaf(tv.w, tf, fmaf(cv.w, rem, bv.w + pv[i].w));
+#pragma unroll
+        for (int p = 0; p < NPL; ++p)
+          s[p] = dot4(qv, make_float4(kreg[p][4 * i], kreg[p][4 * i + 1], kreg[p][4 * i + 2], kreg[p][4 * i + 3]), s[p]);
       }
     }
 
-    // (3) compatibilities of my nodes with head h (K' already holds the 1/sqrt(16))
-    float s[NPL];
+    // (4) feasibility of node tid (+256k): state_agh.py:148-174, exact dtypes; one node per thread, the
+    //     32-node words are published through shared memory
 #pragma unroll
-    for (int p = 0; p < NPL; ++p) {
-      const int j = lane + 32 * p;
-      float acc = 0.f;
-      if (j < n) {
-        const float4* kr = reinterpret_cast<const float4*>(Km + (size_t)j * KS + h * HD);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc = dot4(make_float4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]), kr[i], acc);
-      }
-      s[p] = acc;
-    }
-
-    // (4) feasibility mask: state_agh.py:148-174, exact dtypes
-    bool m[NPL];
-    bool feas_any = false;
-#pragma unroll
-    for (int p = 0; p < NPL; ++p) {
-      const int j = lane + 32 * p;
+    for (int k = 0; k < MPT; ++k) {
+      const int j = tid + 256 * k;
       bool mj = true;
       if (j < n && j >= 1) {
-        const bool cap = __fadd_rn(demj[p], used) > 1.0f;
-        const float tt = __fdiv_rn(dd[p], 110.0f);
-        const double fin = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)twlj[p]), durj[p]);
-        const bool tw = fin > twrj[p];
-        mj = ((vw[p] >> lane) & 1u) | cap | tw;
-        feas_any |= !mj;
+        const bool cap = __fadd_rn(demm[k], used) > 1.0f;
+        const float tt = __fdiv_rn(ddm[k], 110.0f);
+        const double fin = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)twlm[k]), durm[k]);
+        mj = vis[k] | cap | (fin > twrm[k]);
       }
-      m[p] = mj;
+      const uint32_t word = __ballot_sync(0xffffffffu, mj);
+      if (j < NPAD) {
+        if (lane == 0) s_mw[warp + 8 * k] = word;
+        dc[j] = ddm[k];
+      }
     }
-    const bool anyf = __any_sync(0xffffffffu, feas_any);
-    if (lane == 0) m[0] = (prev == 0) && anyf;      // depot: state_agh.py:173
+    __syncthreads();   // (C) mask words + distances of this step visible
+
     uint32_t mw[NPL];
+    uint32_t feas = 0u;
 #pragma unroll
-    for (int p = 0; p < NPL; ++p) mw[p] = __ballot_sync(0xffffffffu, m[p]);
+    for (int p = 0; p < NPL; ++p) {
+      mw[p] = s_mw[p];
+      feas |= (p == 0) ? (~mw[p] & 0xfffffffeu) : ~mw[p];
+    }
+    mw[0] = (mw[0] & 0xfffffffeu) | ((prev == 0 && feas != 0u) ? 1u : 0u);      // depot: state_agh.py:173
     if (warp == 0) {
-      float* dc = s_dcur + (t & 1) * NPAD;
-#pragma unroll
-      for (int p = 0; p < NPL; ++p) dc[lane + 32 * p] = dd[p];
       if (a.mask_dump != nullptr && lane < nwords) a.mask_dump[(trow + t) * nwords + lane] = pick_word<NPL>(mw, lane);
       if (lane == 0) {
         if (a.used_dump != nullptr) a.used_dump[trow + t] = used;
@@ -284,7 +323,7 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
     float mx = -CUDART_INF_F;
 #pragma unroll
     for (int p = 0; p < NPL; ++p) {
-      s[p] = m[p] ? -CUDART_INF_F : s[p];
+      s[p] = ((mw[p] >> lane) & 1u) ? -CUDART_INF_F : s[p];
       mx = fmaxf(mx, s[p]);
     }
 #pragma unroll
@@ -292,7 +331,7 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
     float e[NPL], esum = 0.f;
 #pragma unroll
     for (int p = 0; p < NPL; ++p) {
-      e[p] = m[p] ? 0.f : expf(s[p] - mx);
+      e[p] = expf(s[p] - mx);            // exp(-inf) = 0 for masked nodes; mx is finite (some node is feasible)
       esum += e[p];
     }
 #pragma unroll
@@ -306,10 +345,10 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
     for (int p = 0; p < NPL; ++p) {
       const int j = lane + 32 * p;
       if (j < n) {
-        const float4* vr = reinterpret_cast<const float4*>(Vm + (size_t)j * KS + h * HD);
+        const float4* vr = reinterpret_cast<const float4*>(Vm + (size_t)j * KS);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 v = vr[i];
+          const float4 v = vr[swz(h * 4 + i, j)];
           acc[4 * i + 0] = fmaf(e[p], v.x, acc[4 * i + 0]);
           acc[4 * i + 1] = fmaf(e[p], v.y, acc[4 * i + 1]);
           acc[4 * i + 2] = fmaf(e[p], v.z, acc[4 * i + 2]);
@@ -340,17 +379,15 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
         r1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
       }
       r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
-      // lane now owns element (b4 b3 b2 b1) = 8*b4 + 4*b3 + 2*b2 + b1 of o_h
-      if ((lane & 1) == 0) s_o[h * HD + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] =
-          __fdiv_rn(r1, esum);
+      // lane now owns element lane >> 1 of o_h
+      if ((lane & 1) == 0) s_o[h * HD + (lane >> 1)] = __fdiv_rn(r1, esum);
     }
     __syncthreads();   // (A) o complete
 
     // (7) logits for 16 nodes per warp and pass; lanes 0-15 take features 0..63, lanes 16-31 64..127
     const int half = lane >> 4, jj = lane & 15;
     constexpr int NPASS = (NPL * 32 + 127) / 128;
-    float zp[NPASS], scp[NPASS];
-    float wm = -CUDART_INF_F;
+    float zp[NPASS];
     float best_sc = -CUDART_INF_F, best_z = 0.f;
     int best_j = 0x7fffffff;
 #pragma unroll
@@ -358,20 +395,25 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
       const int j = ps * 128 + warp * 16 + jj;
       float u = 0.f;
       if (j < n) {
-        const float4* lr = reinterpret_cast<const float4*>(Lm + (size_t)j * KS + half * 64);
+        const float4* lr = reinterpret_cast<const float4*>(Lm + (size_t)j * KS);
         const float4* o4 = reinterpret_cast<const float4*>(s_o + half * 64);
-        float u0 = 0.f, u1 = 0.f;
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          u0 = dot4(o4[i], lr[i], u0);
-          u1 = dot4(o4[i + 1], lr[i + 1], u1);
+        for (int i = 0; i < 16; i += 4) {
+          u0 = dot4(o4[i], lr[swz(half * 16 + i, j)], u0);
+          u1 = dot4(o4[i + 1], lr[swz(half * 16 + i + 1, j)], u1);
+          u2 = dot4(o4[i + 2], lr[swz(half * 16 + i + 2, j)], u2);
+          u3 = dot4(o4[i + 3], lr[swz(half * 16 + i + 3, j)], u3);
         }
-        u = u0 + u1;
+        u = (u0 + u1) + (u2 + u3);
       }
       u += __shfl_xor_sync(0xffffffffu, u, 16);
       const bool mj = (j >= n) || ((pick_word<NPL>(mw, j >> 5) >> (j & 31)) & 1u);
       float z = -CUDART_INF_F;
-      if (!mj) z = __fdiv_rn(10.0f * tanhf(u), a.temp);      // attention_model.py:580, :447
+      if (!mj) {
+        z = 10.0f * tanhf(u);                                   // attention_model.py:580
+        if (!unit_temp) z = __fdiv_rn(z, a.temp);               // :447
+      }
       if (half == 0 && j < n) s_z[j] = z;
       float sc = z;
       if (a.inject_logp != nullptr) {
@@ -380,13 +422,16 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
         sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
       }
       zp[ps] = (half == 0) ? z : -CUDART_INF_F;
-      scp[ps] = sc;
-      wm = fmaxf(wm, zp[ps]);
       if (half == 0 && sc > best_sc) { best_sc = sc; best_j = j; best_z = z; }
     }
+    float wm = shift, ws = 0.f;
+    if (!fixed_shift) {
+      wm = -CUDART_INF_F;
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
-    float ws = 0.f;
+      for (int ps = 0; ps < NPASS; ++ps) wm = fmaxf(wm, zp[ps]);
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+    }
 #pragma unroll
     for (int ps = 0; ps < NPASS; ++ps) ws += (zp[ps] == -CUDART_INF_F) ? 0.f : expf(zp[ps] - wm);
 #pragma unroll
@@ -399,28 +444,38 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
     }
     if (lane == 0) {
       float4* r = reinterpret_cast<float4*>(s_red + warp * 8);
-      r[0] = make_float4(wm, ws, best_sc, __int_as_float(best_j));
-      r[1] = make_float4(best_z, 0.f, 0.f, 0.f);
+      r[0] = make_float4(ws, best_sc, __int_as_float(best_j), best_z);
+      r[1] = make_float4(wm, 0.f, 0.f, 0.f);
     }
     __syncthreads();   // (B) per-warp partials complete
 
     // (8) merge, select, update (every thread, redundantly): attention_model.py:446-447,372-390; state_agh.py:99-137
-    float M = -CUDART_INF_F;
+    float M = shift, S = 0.f;
     float g_sc = -CUDART_INF_F, g_z = 0.f;
     int sel = 0x7fffffff;
-    float wms[8], wss[8];
+    if (fixed_shift) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const float4 r0 = reinterpret_cast<const float4*>(s_red + w * 8)[0];
-      const float4 r1v = reinterpret_cast<const float4*>(s_red + w * 8)[1];
-      wms[w] = r0.x; wss[w] = r0.y;
-      M = fmaxf(M, r0.x);
-      const int oj = __float_as_int(r0.w);
-      if (r0.z > g_sc || (r0.z == g_sc && oj < sel)) { g_sc = r0.z; sel = oj; g_z = r1v.x; }
+      for (int w = 0; w < 8; ++w) {
+        const float4 r0 = reinterpret_cast<const float4*>(s_red + w * 8)[0];
+        S += r0.x;
+        const int oj = __float_as_int(r0.z);
+        if (r0.y > g_sc || (r0.y == g_sc && oj < sel)) { g_sc = r0.y; sel = oj; g_z = r0.w; }
+      }
+    } else {
+      float wms[8], wss[8];
+      M = -CUDART_INF_F;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float4 r0 = reinterpret_cast<const float4*>(s_red + w * 8)[0];
+        wss[w] = r0.x;
+        wms[w] = s_red[w * 8 + 4];
+        M = fmaxf(M, wms[w]);
+        const int oj = __float_as_int(r0.z);
+        if (r0.y > g_sc || (r0.y == g_sc && oj < sel)) { g_sc = r0.y; sel = oj; g_z = r0.w; }
+      }
+#pragma unroll
+      for (int w = 0; w < 8; ++w) S += (wms[w] == -CUDART_INF_F) ? 0.f : wss[w] * expf(wms[w] - M);
     }
-    float S = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) S += (wms[w] == -CUDART_INF_F) ? 0.f : wss[w] * expf(wms[w] - M);
     const float logS = logf(S);
     if (replay) {
       sel = (int)a.actions[trow + t];
@@ -432,24 +487,21 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
       for (int j = tid; j < n; j += 256) a.logp_full[(trow + t) * n + j] = (s_z[j] - M) - logS;
     }
 
-    const float d = s_dcur[(t & 1) * NPAD + sel];
+    const float d = dc[sel];
     len = __fadd_rn(len, d);
     if (sel != 0) {
       used = __fadd_rn(used, s_dem[sel]);
       const float tt = __fdiv_rn(d, 110.0f);
       cft = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)s_twl[sel]), s_dur[sel]);
+      ++nvis;
     } else {
       used = 0.f;
       cft = -60.0;
+      nvis += depot_seen ? 0 : 1;
+      depot_seen = true;
     }
-    {
-      const uint32_t bit = 1u << (sel & 31);
-      const int wsel = sel >> 5;
 #pragma unroll
-      for (int p = 0; p < NPL; ++p) {
-        if (wsel == p) { nvis += (vw[p] & bit) ? 0 : 1; vw[p] |= bit; }
-      }
-    }
+    for (int k = 0; k < MPT; ++k) vis[k] |= (sel == tid + 256 * k);
     if (tid == 0) {
       s_serve[sel] = (float)cft;
       a.pi[trow + t] = (int16_t)sel;
@@ -474,27 +526,43 @@ __global__ void __launch_bounds__(256, (NPL == 1 ? 3 : (NPL == 2 ? 2 : 1))) deco
   }
 }
 
-template <int NPL, int NSM>
+template <int NPL, int RES>
 static int launch_decode(const agh_decode_args& a, cudaStream_t st) {
   const int n = a.N + 1;
-  const DecodeSmem L = decode_smem_layout(n, NPL, NSM);
-  auto kern = decode_kernel<NPL, NSM>;
+  const DecodeSmem L = decode_smem_layout(n, NPL, RES);
+  auto kern = decode_kernel<NPL, RES>;
   AGH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   kern<<<a.B, 256, L.total, st>>>(a);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
 }
 
+// Pick the residency: the candidate with the most resident CTAs per SM wins (two instances per SM hide
+// each other's step latency), ties go to the candidate that keeps more in shared memory.
 template <int NPL>
-static int dispatch_nsm(const agh_decode_args& a, cudaStream_t st) {
+static int dispatch_res(const agh_decode_args& a, cudaStream_t st) {
   const int n = a.N + 1;
-  int dev = 0, max_smem = 0;
+  int dev = 0, max_smem = 0, sm_smem = 0;
   AGH_CUDA(cudaGetDevice(&dev));
   AGH_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if ((int)decode_smem_layout(n, NPL, 4).total <= max_smem) return launch_decode<NPL, 4>(a, st);
-  if ((int)decode_smem_layout(n, NPL, 3).total <= max_smem) return launch_decode<NPL, 3>(a, st);
-  if ((int)decode_smem_layout(n, NPL, 2).total <= max_smem) return launch_decode<NPL, 2>(a, st);
-  if ((int)decode_smem_layout(n, NPL, 1).total <= max_smem) return launch_decode<NPL, 1>(a, st);
+  AGH_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+  const int cand[4] = {RES_V | RES_L | RES_P, RES_V | RES_L, RES_L, 0};
+  int best = -1, best_ctas = 0;
+  for (int c = 0; c < 4; ++c) {
+    if (a.smem_mats > 0 && cand[c] != (a.smem_mats & 7)) continue;          // explicit override (bitmask)
+    const int bytes = (int)decode_smem_layout(n, NPL, cand[c]).total;
+    if (bytes > max_smem) continue;
+    int ctas = sm_smem / (bytes + 1024);
+    if (ctas > decode_min_blocks(NPL)) ctas = decode_min_blocks(NPL);
+    if (ctas > best_ctas) { best_ctas = ctas; best = cand[c]; }
+  }
+  switch (best) {
+    case RES_V | RES_L | RES_P: return launch_decode<NPL, RES_V | RES_L | RES_P>(a, st);
+    case RES_V | RES_L: return launch_decode<NPL, RES_V | RES_L>(a, st);
+    case RES_L: return launch_decode<NPL, RES_L>(a, st);
+    case 0: return launch_decode<NPL, 0>(a, st);
+    default: break;
+  }
   set_error("agh_decode: N=%d does not fit shared memory (%d bytes available)", a.N, max_smem);
   return AGH_E_UNSUPPORTED;
 }
@@ -516,16 +584,16 @@ extern "C" int agh_decode(const agh_decode_args* args, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int npl = ceil_div(a.N + 1, 32);
   switch (npl) {
-    case 1: return dispatch_nsm<1>(a, st);
-    case 2: return dispatch_nsm<2>(a, st);
-    case 3: return dispatch_nsm<3>(a, st);
-    case 4: return dispatch_nsm<4>(a, st);
-    case 5: return dispatch_nsm<5>(a, st);
-    case 6: return dispatch_nsm<6>(a, st);
-    case 7: return dispatch_nsm<7>(a, st);
-    case 8: return dispatch_nsm<8>(a, st);
-    case 9: return dispatch_nsm<9>(a, st);
-    case 10: return dispatch_nsm<10>(a, st);
+    case 1: return dispatch_res<1>(a, st);
+    case 2: return dispatch_res<2>(a, st);
+    case 3: return dispatch_res<3>(a, st);
+    case 4: return dispatch_res<4>(a, st);
+    case 5: return dispatch_res<5>(a, st);
+    case 6: return dispatch_res<6>(a, st);
+    case 7: return dispatch_res<7>(a, st);
+    case 8: return dispatch_res<8>(a, st);
+    case 9: return dispatch_res<9>(a, st);
+    case 10: return dispatch_res<10>(a, st);
     default: break;
   }
   set_error("agh_decode: N=%d unsupported", a.N);

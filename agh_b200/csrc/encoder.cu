@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
         if (col < 3 * D) {
           const int mat = col / D, c = col % D;
           const int bi = row / g.n, j = row % g.n;
-          *reinterpret_cast<float4*>(g.keys + (((size_t)bi * 3 + mat) * g.n + j) * KS + c) = v;
+          const int c4 = c >> 2, pc4 = (c4 & ~7) | ((c4 ^ j) & 7);       // chunk swizzle, see decode.cu swz()
+          *reinterpret_cast<float4*>(g.keys + (((size_t)bi * 3 + mat) * g.n + j) * KS + pc4 * 4) = v;
         } else {
           *reinterpret_cast<float4*>(g.psc + (size_t)row * D + (col - 3 * D)) = v;
         }

@@ -116,7 +116,7 @@ def encode_layers(wblob, h0) -> torch.Tensor:
 
 
 def precompute(wblob, h, task: FleetTask):
-    """a4: keys [B,3,n,132], psc [B,n,128], qbase [B,128]."""
+    """a4: keys [B,3,n,128], psc [B,n,128], qbase [B,128]."""
     B, n, _ = h.shape
     dev = h.device
     keys = torch.empty(B, 3, n, KS, dtype=torch.float32, device=dev)
@@ -131,7 +131,8 @@ def precompute(wblob, h, task: FleetTask):
 def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.AGH_GREEDY, temp: float = 1.0,
            seed: int = 0, id_offset: int = 0, actions: Optional[torch.Tensor] = None, replay_steps: int = 0,
            reps: int = 1, inject_logp: Optional[torch.Tensor] = None, want_logp_sel: bool = False,
-           want_logp_full: bool = False, want_dumps: bool = False, t_stride: Optional[int] = None):
+           want_logp_full: bool = False, want_dumps: bool = False, t_stride: Optional[int] = None,
+           smem_mats: int = 0):
     """a5-a12 + a14.  `reps` > 1 runs reps*B rollouts sharing the B key sets (sample_many)."""
     Bk, N = task.B, task.N
     n = N + 1
@@ -160,7 +161,7 @@ def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.
         coord=ptr(task.coord, torch.uint8), demand=ptr(task.demand, torch.float32),
         tw_left=ptr(task.tw_left, torch.float32), tw_right=ptr(task.tw_right, torch.float64),
         duration=ptr(task.duration, torch.float64), distance=ptr(distance, torch.float32),
-        wblob=ptr(wblob, torch.float32), key_mod=Bk if reps > 1 else 0, mode=mode, temp=float(temp),
+        wblob=ptr(wblob, torch.float32), key_mod=Bk if reps > 1 else 0, smem_mats=int(smem_mats), mode=mode, temp=float(temp),
         seed=int(seed) & (2 ** 64 - 1), id_offset=int(id_offset), actions=ptr(actions), replay_steps=int(replay_steps),
         inject_logp=ptr(inject_logp), t_stride=T, pi=ptr(out['pi']), steps=ptr(out['steps']), ll=ptr(out['ll']),
         cost=ptr(out['cost']), serve=ptr(out['serve']), logp_sel=ptr(out.get('logp_sel')),

@@ -29,7 +29,7 @@ extern "C" {
 #define AGH_FF 512
 #define AGH_LAYERS 3
 #define AGH_NODE_SIZE 92
-#define AGH_KEY_STRIDE 132 /* floats per node row of the staged K'/V/LK' matrices (528 B, bank-conflict-free) */
+#define AGH_KEY_STRIDE 128 /* floats per node row of the staged K'/V/LK' matrices; 16-byte chunks XOR-swizzled by (node & 7) */
 #define AGH_MAX_N 320
 
 enum {
@@ -94,7 +94,7 @@ int agh_init_embed(const float* wblob, const uint8_t* coord, const float* demand
 int agh_encode_layers(const float* wblob, const float* h0, int B, int N, float* h_out, void* workspace, void* stream);
 
 /* ---- a4: decoder precompute (attention_model.py:392-414,604-611) ---------------------------
- *   h[B][n][128] -> keys[B][3][n][132] (K'/4, V, LK'), psc[B][n][128], qbase[B][128]
+ *   h[B][n][128] -> keys[B][3][n][128] (K'/4, V, LK'), psc[B][n][128], qbase[B][128]
  *   fleet_ids[B] i32 (0..9) or NULL with `fleet` used for every instance.
  */
 int agh_precompute(const float* wblob, const float* h, const int32_t* fleet_ids, int fleet, int B, int N,
@@ -104,7 +104,7 @@ int agh_precompute(const float* wblob, const float* h, const int32_t* fleet_ids,
  *      state_agh.py:60-174), one CTA per instance for all T steps ----------------------------- */
 typedef struct {
   /* inputs */
-  const float* keys;       /* [B][3][n][132] */
+  const float* keys;       /* [B][3][n][128] */
   const float* psc;        /* [B][n][128] */
   const float* qbase;      /* [B][128] */
   const uint8_t* coord;    /* [B][n] */
@@ -117,6 +117,7 @@ typedef struct {
   /* shared-key replication (sample_many, utils/functions.py:171-188): instance r of B uses the
      keys/psc/qbase/node vectors of instance r % key_mod when key_mod > 0 */
   int key_mod;
+  int smem_mats;           /* shared-memory residency: 0 = auto; else 8 | bitmask (1: V, 2: LK', 4: P_sc); the rest is read via L2 */
   int mode;                /* AGH_GREEDY | AGH_SAMPLING | AGH_REPLAY */
   float temp;              /* softmax temperature (attention_model.py:447) */
   uint64_t seed;           /* Philox key; counter = (instance id, step, node) */

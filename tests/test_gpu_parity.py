@@ -378,9 +378,12 @@ def test_training_step_matches_oracle(tables, weights):
     assert np.allclose(torch.stack(lls, 1).detach().cpu().numpy(), np.stack([o['ll'].detach().numpy() for o in outs], 1),
                        rtol=LOGP_RTOL, atol=1e-3)
     assert loss.item() == pytest.approx(ref_loss.item(), rel=1e-3)
+    # biases feeding a train-mode BatchNorm have mathematically zero gradient (pure rounding noise), so the
+    # error is measured against the larger of the tensor's own norm and 1e-5 of the global gradient norm
+    gnorm = np.sqrt(sum(float((W[k].grad ** 2).sum()) for k, _ in model.named_parameters()))
     for k, p in model.named_parameters():
         gm, gr = p.grad.cpu().numpy(), W[k].grad.numpy()
-        denom = np.linalg.norm(gr) + 1e-6
+        denom = max(np.linalg.norm(gr), 1e-5 * gnorm)
         assert np.linalg.norm(gm - gr) / denom < 5e-3, 'gradient of %s differs: %.3e' % (k, np.linalg.norm(gm - gr) / denom)
     # running statistics were updated like the reference's (momentum 0.1, 6 BN layers x 10 fleets)
     assert int(model.state_dict()['embedder.layers.0.1.normalizer.num_batches_tracked']) == 10
