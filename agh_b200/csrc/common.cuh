@@ -36,7 +36,15 @@ constexpr size_t W_FC_T = W_DEC + D * 4 * D;                  // [128][128]
 constexpr size_t W_FLEET = W_FC_T + D * D;                    // [10][128]
 constexpr size_t W_CAP = W_FLEET + 10 * D;                    // [128]
 constexpr size_t W_TIME = W_CAP + D;                          // [128]
-constexpr size_t W_TOTAL = W_TIME + D;
+// K-major ([out][in]) copies of the GEMM weights for the tensor-core path (TMA + tcgen05 want K contiguous)
+constexpr size_t W_TC0 = W_TIME + D;
+constexpr size_t T_WQKV = 0;                                  // [384][128]
+constexpr size_t T_WO = T_WQKV + 3 * D * D;                   // [128][128]
+constexpr size_t T_W1 = T_WO + D * D;                         // [512][128]
+constexpr size_t T_W2 = T_W1 + FF * D;                        // [128][512]
+constexpr size_t T_SIZE = T_W2 + D * FF;
+constexpr size_t W_TC_DEC = W_TC0 + LAYERS * T_SIZE;          // [512][128]
+constexpr size_t W_TOTAL = W_TC_DEC + 4 * D * D;
 
 void set_error(const char* fmt, ...);
 void count_launch();   // agh_launch_count(): kernels launched by this library since load

@@ -11,7 +11,10 @@
 // flash-style kernel: one CTA per (instance, head), K_h/V_h staged in shared memory, one query row
 // per thread with an online softmax, so no [n,n] score matrix ever reaches HBM.
 #include "common.cuh"
+#include "gemm.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace agh {
 
@@ -53,20 +56,6 @@ __global__ void init_embed_kernel(const float* __restrict__ w, const uint8_t* __
 // ------------------------------------------------------------------------------------------
 // SGEMM  C[M,Nc] = epi(A[M,K] @ W[K,Nc])
 // ------------------------------------------------------------------------------------------
-enum { EPI_PLAIN = 0, EPI_BIAS_RELU = 1, EPI_RES_BN = 2, EPI_DEC = 3 };
-
-struct GemmArgs {
-  const float* A; int lda;
-  const float* W;          // [K][Nc] row-major
-  float* C; int ldc;
-  int M, K, Nc;
-  const float* bias;       // [Nc] or null
-  const float* res; int ldr;   // residual
-  const float* bn_s; const float* bn_t;
-  // EPI_DEC
-  float* keys; float* psc; int n;
-};
-
 constexpr int BM = 128, BN = 128, BK = 16, LDA_S = BM + 4;
 
 template <int EPI>
@@ -168,8 +157,19 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
   }
 }
 
+// AGH_GEMM=simt forces the CUDA-core SGEMM (A/B comparisons); default is the tcgen05 path
+static int g_gemm_backend = -1;
+static bool use_tensor_cores() {
+  if (g_gemm_backend < 0) {
+    const char* e = getenv("AGH_GEMM");
+    g_gemm_backend = (e != nullptr && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return g_gemm_backend == 1;
+}
+
 template <int EPI>
 static int launch_gemm(const GemmArgs& g, cudaStream_t st) {
+  if (use_tensor_cores() && g.Wt != nullptr) return launch_gemm_tc<EPI>(g, st);
   dim3 grid(ceil_div(g.M, BM), g.Nc / BN);
   sgemm_kernel<EPI><<<grid, 256, 0, st>>>(g);
   AGH_LAUNCH_CHECK();
@@ -258,6 +258,12 @@ __global__ void __launch_bounds__(128) qbase_kernel(const float* __restrict__ w,
 
 using namespace agh;
 
+extern "C" int agh_set_gemm_backend(int backend) {
+  if (backend != 0 && backend != 1) return AGH_E_ARG;
+  agh::g_gemm_backend = backend;
+  return AGH_OK;
+}
+
 extern "C" size_t agh_encoder_workspace_bytes(int B, int N) {
   // qkv [M][384] + heads [M][128] + x1 [M][128] + hidden [M][512] + xa [M][128]
   const size_t M = (size_t)B * (N + 1);
@@ -293,24 +299,25 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
   if (mha_smem > 48 * 1024) AGH_CUDA(cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mha_smem));
   for (int l = 0; l < LAYERS; ++l) {
     const float* lw = wblob + W_LAYER0 + (size_t)l * L_SIZE;
+    const float* tw = wblob + W_TC0 + (size_t)l * T_SIZE;
     float* xout = (l == LAYERS - 1) ? h_out : xa;
     GemmArgs g{};
-    g.A = x; g.lda = D; g.W = lw + L_WQKV; g.C = qkv; g.ldc = 3 * D; g.M = M; g.K = D; g.Nc = 3 * D;
+    g.A = x; g.lda = D; g.W = lw + L_WQKV; g.Wt = tw + T_WQKV; g.C = qkv; g.ldc = 3 * D; g.M = M; g.K = D; g.Nc = 3 * D;
     int rc = launch_gemm<EPI_PLAIN>(g, st);
     if (rc) return rc;
     mha_kernel<<<B * H, mha_threads, mha_smem, st>>>(qkv, n, heads);
     AGH_LAUNCH_CHECK();
     g = GemmArgs{};
-    g.A = heads; g.lda = D; g.W = lw + L_WO; g.C = x1; g.ldc = D; g.M = M; g.K = D; g.Nc = D;
+    g.A = heads; g.lda = D; g.W = lw + L_WO; g.Wt = tw + T_WO; g.C = x1; g.ldc = D; g.M = M; g.K = D; g.Nc = D;
     g.res = x; g.ldr = D; g.bn_s = lw + L_BN1S; g.bn_t = lw + L_BN1T;
     rc = launch_gemm<EPI_RES_BN>(g, st);
     if (rc) return rc;
     g = GemmArgs{};
-    g.A = x1; g.lda = D; g.W = lw + L_W1T; g.C = hid; g.ldc = FF; g.M = M; g.K = D; g.Nc = FF; g.bias = lw + L_B1;
+    g.A = x1; g.lda = D; g.W = lw + L_W1T; g.Wt = tw + T_W1; g.C = hid; g.ldc = FF; g.M = M; g.K = D; g.Nc = FF; g.bias = lw + L_B1;
     rc = launch_gemm<EPI_BIAS_RELU>(g, st);
     if (rc) return rc;
     g = GemmArgs{};
-    g.A = hid; g.lda = FF; g.W = lw + L_W2T; g.C = xout; g.ldc = D; g.M = M; g.K = FF; g.Nc = D; g.bias = lw + L_B2;
+    g.A = hid; g.lda = FF; g.W = lw + L_W2T; g.Wt = tw + T_W2; g.C = xout; g.ldc = D; g.M = M; g.K = FF; g.Nc = D; g.bias = lw + L_B2;
     g.res = x1; g.ldr = D; g.bn_s = lw + L_BN2S; g.bn_t = lw + L_BN2T;
     rc = launch_gemm<EPI_RES_BN>(g, st);
     if (rc) return rc;
@@ -343,7 +350,7 @@ extern "C" int agh_precompute(const float* wblob, const float* h, const int32_t*
   cudaStream_t st = (cudaStream_t)stream;
   const int n = N + 1;
   GemmArgs g{};
-  g.A = h; g.lda = D; g.W = wblob + W_DEC; g.M = B * n; g.K = D; g.Nc = 4 * D; g.keys = keys; g.psc = psc; g.n = n;
+  g.A = h; g.lda = D; g.W = wblob + W_DEC; g.Wt = wblob + W_TC_DEC; g.M = B * n; g.K = D; g.Nc = 4 * D; g.keys = keys; g.psc = psc; g.n = n;
   int rc = launch_gemm<EPI_DEC>(g, st);
   if (rc) return rc;
   qbase_kernel<<<B, D, 0, st>>>(wblob, h, fleet_ids, fleet, n, qbase);

@@ -1,0 +1,25 @@
+// Shared declarations of the two GEMM back ends (CUDA-core SGEMM in encoder.cu, tcgen05 in gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace agh {
+
+enum { EPI_PLAIN = 0, EPI_BIAS_RELU = 1, EPI_RES_BN = 2, EPI_DEC = 3 };
+
+struct GemmArgs {
+  const float* A; int lda;
+  const float* W;          // [K][Nc] row-major   (CUDA-core path)
+  const float* Wt;         // [Nc][K] row-major   (tensor-core path, K-major)
+  float* C; int ldc;
+  int M, K, Nc;
+  const float* bias;       // [Nc] or null
+  const float* res; int ldr;   // residual
+  const float* bn_s; const float* bn_t;
+  // EPI_DEC: scatter into the decode kernel's key layout
+  float* keys; float* psc; int n;
+};
+
+template <int EPI>
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+
+}  // namespace agh

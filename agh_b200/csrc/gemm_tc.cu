@@ -1,0 +1,497 @@
+// Tensor-core GEMM for the encoder / precompute contractions:  C[M,Nc] = epi(A[M,K] @ W[Nc,K]^T), fp32 in,
+// fp32 out, computed on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) with the 3xTF32 split
+//      a = a_hi + a_lo,  w = w_hi + w_lo   (hi = rn_tf32(x), lo = rn_tf32(x - hi))
+//      a.w ~= a_hi.w_hi + a_hi.w_lo + a_lo.w_hi            (dropped term ~2^-22 relative)
+// so the result keeps fp32-level accuracy (the 1e-4 log-prob tolerance rules out plain tf32 / bf16).
+//
+// Persistent, warp-specialised kernel: each CTA owns one 128-column slab of W and loops over 128-row tiles of A.
+//   warp 0      : TMA producer  - cp.async.bulk.tensor (SWIZZLE_128B) of [128 x 32] fp32 blocks into a 3-stage ring
+//   warp 1      : MMA issuer    - one elected lane issues 3 tcgen05.mma.kind::tf32 per K=8 step; tcgen05.commit
+//                                 releases the smem stage / hands the TMEM accumulator to the epilogue
+//   warps 2..5  : splitters     - hi/lo split of the landed fp32 blocks in shared memory (element-wise, so the TMA
+//                                 swizzle is irrelevant), fence.proxy.async
+//   warps 6..9  : epilogue      - tcgen05.ld -> bias / ReLU / residual + BatchNorm / key scatter -> HBM, overlapped
+//                                 with the next tile's main loop through a double-buffered TMEM accumulator
+// K = 128 (QKV, out-projection, FF1, decoder projection): the W slab (hi + lo, 128 KB) is loaded and split ONCE
+// per CTA and stays resident; only A streams.  K = 512 (FF2): W blocks stream with A.
+//
+// The tensor core adds into its fp32 accumulator with truncation, so the error grows with the number of sequential
+// accumulations: the small cross terms go to their own accumulator (and, for K = 512, the hi.hi terms are spread
+// round-robin over three), and the epilogue adds the accumulators in fp32 round-to-nearest.
+//
+// Replaces the cuBLAS calls behind graph_encoder.py:83-86,106-109,165-168 and attention_model.py:405-406.
+#include "common.cuh"
+#include "gemm.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace agh {
+
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;             // BK fp32 = 128 bytes = one swizzle-128B row
+constexpr int BLK = BM * BK * 4;                       // one [128 x 32] fp32 block = 16 KB
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 320;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// wait until the phase with the given parity has completed (a fresh barrier has "completed" parity 1)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "@%%px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
+// 8-row atoms of 128 B rows, atoms 1024 B apart (SBO), LBO unused for swizzled K-major.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                               // leading byte offset (>>4), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset (>>4), bits [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));      // the caller issues tcgen05.wait::ld before reading r[]
+}
+
+// x = hi + lo with hi = rn_tf32(x) and lo = rn_tf32(x - hi): both exactly representable in tf32 (so it does not
+// matter whether the tensor core truncates or rounds its fp32 containers) and the rounding errors are unbiased.
+// Round-to-nearest (ties away) with an integer add + mask: cvt.rna.tf32.f32 runs on the slow conversion pipe.
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+// split `nvec` float4 starting at `hi_ptr` in place, writing the remainders to `lo_ptr` (same element order)
+__device__ __forceinline__ void split_block(unsigned char* hi_ptr, unsigned char* lo_ptr, int nvec, int t) {
+#pragma unroll 4
+  for (int i = t; i < nvec; i += 128) {
+    float4* ph = reinterpret_cast<float4*>(hi_ptr) + i;
+    const float4 v = *ph;
+    float4 hi, lo;
+    hi.x = rn_tf32(v.x); lo.x = rn_tf32(v.x - hi.x);
+    hi.y = rn_tf32(v.y); lo.y = rn_tf32(v.y - hi.y);
+    hi.z = rn_tf32(v.z); lo.z = rn_tf32(v.z - hi.z);
+    hi.w = rn_tf32(v.w); lo.w = rn_tf32(v.w - hi.w);
+    *ph = hi;
+    *(reinterpret_cast<float4*>(lo_ptr) + i) = lo;
+  }
+}
+
+// WRES = true : K == 128, W slab resident (hi 64 KB + lo 64 KB), stage = A hi|lo (32 KB), 2 TMEM buffers of {main, cross}
+// WRES = false: K % 32 == 0, stage = A hi|lo + W hi|lo (64 KB), 1 TMEM buffer of {3 main, cross}
+template <bool WRES>
+struct Cfg {
+  static constexpr int STAGE_BYTES = WRES ? 2 * BLK : 4 * BLK;
+  static constexpr int WRES_BYTES = WRES ? 8 * BLK : 0;
+  static constexpr int NACC = WRES ? 1 : 3;
+  static constexpr int NBUF = WRES ? 2 : 1;
+  static constexpr int NBARS = 3 * STAGES + 2 * NBUF + 2;
+  static constexpr int SMEM = WRES_BYTES + STAGES * STAGE_BYTES + 1024 /*align*/ + 8 * NBARS + 16;
+};
+
+template <int EPI, bool WRES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
+  using C = Cfg<WRES>;
+  extern __shared__ unsigned char smem_raw[];
+  // swizzle-128B tiles need 1024-byte alignment
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* wres = smem;                                   // [4 k-blocks hi][4 k-blocks lo] when WRES
+  unsigned char* ring = smem + C::WRES_BYTES;
+  unsigned char* bars = ring + STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = smem_u32(bars);
+  auto bar_raw = [&](int s) { return bar_base + 8 * s; };                       // TMA -> splitters
+  auto bar_split = [&](int s) { return bar_base + 8 * (STAGES + s); };          // splitters -> MMA
+  auto bar_empty = [&](int s) { return bar_base + 8 * (2 * STAGES + s); };      // MMA -> TMA
+  auto bar_tfull = [&](int b) { return bar_base + 8 * (3 * STAGES + b); };      // MMA -> epilogue
+  auto bar_tempty = [&](int b) { return bar_base + 8 * (3 * STAGES + C::NBUF + b); };   // epilogue -> MMA
+  const uint32_t bar_wraw = bar_base + 8 * (3 * STAGES + 2 * C::NBUF);
+  const uint32_t bar_wsplit = bar_wraw + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 * C::NBARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BN;
+  const int nkb = g.K / BK;
+  const int num_mt = (g.M + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_raw(s), 1);
+      mbar_init(bar_split(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int b = 0; b < C::NBUF; ++b) {
+      mbar_init(bar_tfull(b), 1);
+      mbar_init(bar_tempty(b), 4);
+    }
+    mbar_init(bar_wraw, 1);
+    mbar_init(bar_wsplit, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation (whole warp): all 512 columns, one CTA per SM
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int ACC_COLS = (C::NACC + 1) * BN;                  // TMEM columns of one accumulator set
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      if (WRES) {
+        mbar_expect_tx(bar_wraw, 4 * BLK);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem_u32(wres + kb * BLK), &tmW, bar_wraw, kb * BK, n0);
+      }
+      uint32_t it = 0;
+      for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_empty(s), ((it / STAGES) & 1) ^ 1);
+          unsigned char* st = ring + s * C::STAGE_BYTES;
+          mbar_expect_tx(bar_raw(s), WRES ? BLK : 2 * BLK);
+          tma_load_2d(smem_u32(st), &tmA, bar_raw(s), kb * BK, mt * BM);
+          if (!WRES) tma_load_2d(smem_u32(st + 2 * BLK), &tmW, bar_raw(s), kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = umma_idesc(BM, BN);
+    if (WRES) {
+      mbar_wait(bar_wsplit, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    uint32_t it = 0, tile = 0;
+    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++tile) {
+      const int ab = tile % C::NBUF;
+      mbar_wait(bar_tempty(ab), ((tile / C::NBUF) & 1) ^ 1);       // epilogue has drained this accumulator set
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t t_acc = tmem_base + ab * ACC_COLS;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(bar_split(s), (it / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t st = smem_u32(ring + s * C::STAGE_BYTES);
+          const uint64_t da_hi = umma_desc(st), da_lo = umma_desc(st + BLK);
+          const uint32_t wb = WRES ? smem_u32(wres + kb * BLK) : st + 2 * BLK;
+          const uint64_t dw_hi = umma_desc(wb), dw_lo = umma_desc(wb + (WRES ? 4 * BLK : BLK));
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 8 tf32 = 32 bytes inside the swizzle atom
+            const int ks = kb * (BK / 8) + k;
+            const uint32_t t_cross = t_acc + C::NACC * BN;
+            const uint32_t t_main = t_acc + (ks % C::NACC) * BN;
+            umma_tf32(t_cross, da_lo + adv, dw_hi + adv, idesc, ks != 0);
+            umma_tf32(t_cross, da_hi + adv, dw_lo + adv, idesc, 1);
+            umma_tf32(t_main, da_hi + adv, dw_hi + adv, idesc, ks >= C::NACC);
+          }
+          umma_commit(bar_empty(s));                             // frees the stage when these MMAs retire
+          if (kb == nkb - 1) umma_commit(bar_tfull(ab));         // accumulator set complete
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ================= splitters (warps 2..5, 128 threads) =================
+    const int t = threadIdx.x - 64;
+    if (WRES) {
+      mbar_wait(bar_wraw, 0);
+      split_block(wres, wres + 4 * BLK, 4 * BLK / 16, t);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_wsplit);
+    }
+    uint32_t it = 0;
+    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(bar_raw(s), (it / STAGES) & 1);
+        unsigned char* st = ring + s * C::STAGE_BYTES;
+        split_block(st, st + BLK, BLK / 16, t);
+        if (!WRES) split_block(st + 2 * BLK, st + 3 * BLK, BLK / 16, t);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(bar_split(s));
+      }
+    }
+  } else {
+    // ================= epilogue (warps 6..9): TMEM lane quarter = warp % 4, one output row per thread =================
+    const int q = warp & 3;
+    uint32_t tile = 0;
+    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++tile) {
+      const int ab = tile % C::NBUF;
+      mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t t_acc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
+      const int row0 = mt * BM + q * 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float r[32];
+        {
+          uint32_t ra[C::NACC + 1][32];
+#pragma unroll
+          for (int a = 0; a <= C::NACC; ++a) tmem_ld32(t_acc + (uint32_t)(a * BN + c0), ra[a]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float acc = __uint_as_float(ra[0][i]);
+#pragma unroll
+            for (int a = 1; a <= C::NACC; ++a) acc += __uint_as_float(ra[a][i]);
+            r[i] = acc;
+          }
+        }
+        if (c0 == BN - 32) {              // every column of this accumulator set is in registers: hand it back
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty(ab));
+        }
+        if (EPI != EPI_PLAIN) {
+          // row-wise epilogue: this thread owns row `row0 + lane`, 8 x 16-byte accesses per 32-column chunk
+          // (measured faster than the transposed variant below whenever the epilogue reads bias / residual / BN)
+          const int row = row0 + lane;
+          if (row >= g.M) continue;
+          int bi = 0, j = 0;
+          if (EPI == EPI_DEC) { bi = row / g.n; j = row % g.n; }
+#pragma unroll
+          for (int v4 = 0; v4 < 8; ++v4) {
+            const int col = n0 + c0 + v4 * 4;
+            float4 v = make_float4(r[4 * v4], r[4 * v4 + 1], r[4 * v4 + 2], r[4 * v4 + 3]);
+            if (EPI == EPI_BIAS_RELU) {
+              const float4 bb = *reinterpret_cast<const float4*>(g.bias + col);
+              v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f); v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
+            } else if (EPI == EPI_RES_BN) {
+              if (g.bias != nullptr) {
+                const float4 bb = *reinterpret_cast<const float4*>(g.bias + col);
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              }
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(g.res + (size_t)row * g.ldr + col));
+              const float4 sc = *reinterpret_cast<const float4*>(g.bn_s + col);
+              const float4 sh = *reinterpret_cast<const float4*>(g.bn_t + col);
+              v.x = fmaf(rr.x + v.x, sc.x, sh.x); v.y = fmaf(rr.y + v.y, sc.y, sh.y);
+              v.z = fmaf(rr.z + v.z, sc.z, sh.z); v.w = fmaf(rr.w + v.w, sc.w, sh.w);
+            }
+            if (EPI == EPI_DEC) {
+              if (col < 3 * D) {
+                const int mat = col / D, c = col % D;
+                const int c4 = c >> 2, pc4 = (c4 & ~7) | ((c4 ^ j) & 7);       // chunk swizzle, see decode.cu swz()
+                *reinterpret_cast<float4*>(g.keys + (((size_t)bi * 3 + mat) * g.n + j) * KS + pc4 * 4) = v;
+              } else {
+                *reinterpret_cast<float4*>(g.psc + (size_t)row * D + (col - 3 * D)) = v;
+              }
+            } else {
+              *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + col) = v;
+            }
+          }
+          continue;
+        }
+        // EPI_PLAIN: 32x32 in-register transpose (5 butterfly stages): before, lane = row and r[c] = column c; after,
+        // lane = column and r[i] = row i, so that every store below is one coalesced 128-byte line per row
+#pragma unroll
+        for (int k = 16; k >= 1; k >>= 1) {
+          const bool up = (lane & k) != 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if ((i & k) == 0) {
+              const float send = up ? r[i] : r[i + k];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, k);
+              if (up) r[i] = recv; else r[i + k] = recv;
+            }
+          }
+        }
+        const int col = n0 + c0 + lane;
+        float bias = 0.f, sc = 1.f, sh = 0.f;
+        if (EPI == EPI_BIAS_RELU || (EPI == EPI_RES_BN && g.bias != nullptr)) bias = g.bias[col];
+        if (EPI == EPI_RES_BN) { sc = g.bn_s[col]; sh = g.bn_t[col]; }
+        int mat = 0, cc = 0, bi = 0, j = 0;
+        if (EPI == EPI_DEC) { mat = col / D; cc = col % D; bi = row0 / g.n; j = row0 % g.n; }
+        float rr[32];
+        if (EPI == EPI_RES_BN) {          // all residual loads first: 32 independent coalesced 128-byte reads in flight
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rr[i] = (row0 + i < g.M) ? __ldg(g.res + (size_t)(row0 + i) * g.ldr + col) : 0.f;
+        }
+#pragma unroll      // full unroll: r[] must stay in registers (static indices only)
+        for (int i = 0; i < 32; ++i) {
+          const int row = row0 + i;
+          float v = r[i];
+          if (EPI == EPI_BIAS_RELU) {
+            v = fmaxf(v + bias, 0.f);
+          } else if (EPI == EPI_RES_BN) {
+            v = fmaf(rr[i] + (v + bias), sc, sh);
+          }
+          if (row < g.M) {
+            if (EPI == EPI_DEC) {
+              if (mat < 3) {
+                const int c4 = cc >> 2, pc4 = (c4 & ~7) | ((c4 ^ j) & 7);       // chunk swizzle, see decode.cu swz()
+                g.keys[(((size_t)bi * 3 + mat) * g.n + j) * KS + pc4 * 4 + (cc & 3)] = v;
+              } else {
+                g.psc[(size_t)row * D + cc] = v;
+              }
+            } else {
+              g.C[(size_t)row * g.ldc + col] = v;
+            }
+          }
+          if (EPI == EPI_DEC) { if (++j == g.n) { j = 0; ++bi; } }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D fp32 row-major [rows][cols] (row pitch ld floats), box = [128 rows][32 floats], 128-byte swizzle, OOB -> 0
+static int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return AGH_E_CUDA;
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)rc, (unsigned long long)rows,
+              (unsigned long long)cols, (unsigned long long)ld);
+    return AGH_E_CUDA;
+  }
+  return AGH_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int EPI, bool WRES>
+static int launch_cfg(const GemmArgs& g, cudaStream_t st) {
+  using C = Cfg<WRES>;
+  CUtensorMap tmA, tmW;
+  int rc = make_map(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda);
+  if (rc) return rc;
+  rc = make_map(&tmW, g.Wt, (uint64_t)g.Nc, (uint64_t)g.K, (uint64_t)g.K);
+  if (rc) return rc;
+  auto kern = gemm_tc_kernel<EPI, WRES>;
+  AGH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  const int n_tiles = g.Nc / BN, m_tiles = ceil_div(g.M, BM);
+  int per_slab = sm_count() / n_tiles;                 // persistent: one CTA per SM, CTAs of a slab stride over the row tiles
+  if (per_slab < 1) per_slab = 1;
+  if (per_slab > m_tiles) per_slab = m_tiles;
+  dim3 grid(per_slab, n_tiles);
+  kern<<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmW, g);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+}  // namespace tc
+
+template <int EPI>
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+  if (g.K % tc::BK != 0 || (g.lda % 4) != 0 || g.Nc % tc::BN != 0 || g.M <= 0) {
+    set_error("gemm_tc: unsupported M=%d K=%d Nc=%d lda=%d", g.M, g.K, g.Nc, g.lda);
+    return AGH_E_UNSUPPORTED;
+  }
+  if (g.K == 128) return tc::launch_cfg<EPI, true>(g, st);
+  return tc::launch_cfg<EPI, false>(g, st);
+}
+
+template int launch_gemm_tc<EPI_PLAIN>(const GemmArgs&, cudaStream_t);
+template int launch_gemm_tc<EPI_BIAS_RELU>(const GemmArgs&, cudaStream_t);
+template int launch_gemm_tc<EPI_RES_BN>(const GemmArgs&, cudaStream_t);
+template int launch_gemm_tc<EPI_DEC>(const GemmArgs&, cudaStream_t);
+
+}  // namespace agh

@@ -23,17 +23,20 @@ BN_EPS = 1e-5
 
 def blob_floats() -> int:
     layer = D * 3 * D + D * D + 2 * D + D * FF + FF + FF * D + D + 2 * D
-    return 92 * D + 3 * D + D + LAYERS * layer + D * 4 * D + D * D + 10 * D + 2 * D
+    tc = LAYERS * (3 * D * D + D * D + FF * D + D * FF) + 4 * D * D      # K-major copies for the tcgen05 GEMMs
+    return 92 * D + 3 * D + D + LAYERS * layer + D * 4 * D + D * D + 10 * D + 2 * D + tc
 
 
 def pack_weights(sd: Dict[str, torch.Tensor], device=None) -> torch.Tensor:
     g = lambda k: sd[k].detach().to(device=device, dtype=torch.float64)
     parts = [g('loc_embedding.weight'), g('init_embed.weight').t(), g('init_embed.bias')]
+    tc_parts = []
     for l in range(LAYERS):
         pre = 'embedder.layers.%d.' % l
         heads = lambda k: g(pre + '0.module.' + k).permute(1, 0, 2).reshape(D, D)       # [c][h*16+k]
         parts.append(torch.cat((heads('W_query'), heads('W_key'), heads('W_val')), 1))   # [128][384]
         parts.append(g(pre + '0.module.W_out').reshape(D, D))                            # [h*16+k][c]
+        tc_parts += [parts[-2].t(), parts[-1].t(), g(pre + '2.module.0.weight'), g(pre + '2.module.2.weight')]
         s1 = g(pre + '1.normalizer.weight') / torch.sqrt(g(pre + '1.normalizer.running_var') + BN_EPS)
         t1 = g(pre + '1.normalizer.bias') - g(pre + '1.normalizer.running_mean') * s1
         parts += [s1, t1]
@@ -48,6 +51,7 @@ def pack_weights(sd: Dict[str, torch.Tensor], device=None) -> torch.Tensor:
     lk_fold = (wout.t() @ wn[2 * D:3 * D]) / math.sqrt(D)    # [c][e]
     wdec = torch.cat((wn[0:D].t() / math.sqrt(D // H), wn[D:2 * D].t(), lk_fold.t(), wsc[:, :D].t()), 1)   # [128][512]
     parts += [wdec, g('project_fixed_context.weight').t(), g('fleets_embedding.weight'), wsc[:, D], wsc[:, D + 1]]
+    parts += tc_parts + [wdec.t()]
     blob = torch.cat([p.contiguous().reshape(-1) for p in parts]).to(torch.float32).contiguous()
     assert blob.numel() == blob_floats(), (blob.numel(), blob_floats())
     return blob

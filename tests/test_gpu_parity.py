@@ -387,3 +387,31 @@ def test_training_step_matches_oracle(tables, weights):
         assert np.linalg.norm(gm - gr) / denom < 5e-3, 'gradient of %s differs: %.3e' % (k, np.linalg.norm(gm - gr) / denom)
     # running statistics were updated like the reference's (momentum 0.1, 6 BN layers x 10 fleets)
     assert int(model.state_dict()['embedder.layers.0.1.normalizer.num_batches_tracked']) == 10
+
+
+@pytest.mark.parametrize('n,B', [(20, 7), (100, 300), (50, 1000)])
+def test_tensor_core_gemm_matches_cuda_core(cuda_model, tables, n, B):
+    """tcgen05 3xTF32 GEMMs (encoder + precompute) against the fp32 CUDA-core SGEMM path: fp32-level agreement,
+    including ragged last row tiles (M = B*(n+1) is not a multiple of 128)."""
+    from agh_b200 import ops, _lib
+    inst = {k: v[:B] for k, v in make_instances(n).items()}
+    task = to_task(O.fleet_task(tables, inst, 5, O.new_tw_left_levels(inst)))
+    blob = cuda_model.weight_blob()
+    lib = _lib.lib()
+    try:
+        lib.agh_set_gemm_backend(0)
+        h_s = ops.encode(blob, task)
+        keys_s, psc_s, qb_s = ops.precompute(blob, h_s, task)
+        lib.agh_set_gemm_backend(1)
+        h_t = ops.encode(blob, task)
+        keys_t, psc_t, qb_t = ops.precompute(blob, h_s, task)
+        torch.cuda.synchronize()
+    finally:
+        lib.agh_set_gemm_backend(1)
+    # 12 chained GEMMs; |h| reaches ~13, so 6e-5 absolute is ~5e-6 relative (the tensor core accumulates with
+    # truncation; gemm_tc.cu keeps the chains short with separate accumulators)
+    err_h = (h_t - h_s).abs().max().item()
+    assert err_h < 6e-5, 'encoder: tensor-core vs CUDA-core max abs err %.3e' % err_h
+    assert (h_t - h_s).abs().mean().item() < 5e-6
+    assert (keys_t - keys_s).abs().max().item() < 3e-5
+    assert (psc_t - psc_s).abs().max().item() < 3e-5

@@ -74,7 +74,8 @@ def test_bad_arguments_return_error_codes():
 # ------------------------------------------------------------------ weight folds
 def _split_blob(blob):
     D, FF = 128, 512
-    it = iter([92 * D, 3 * D, D] + [D * 3 * D, D * D, D, D, D * FF, FF, FF * D, D, D, D] * 3 + [D * 4 * D, D * D, 10 * D, D, D])
+    it = iter([92 * D, 3 * D, D] + [D * 3 * D, D * D, D, D, D * FF, FF, FF * D, D, D, D] * 3 + [D * 4 * D, D * D, 10 * D, D, D] +
+              [3 * D * D, D * D, FF * D, D * FF] * 3 + [4 * D * D])
     out, off = [], 0
     for sz in it:
         out.append(blob[off:off + sz]); off += sz
@@ -96,6 +97,12 @@ def test_weight_folds_reproduce_the_oracle(weights, tables):
         if k.endswith('normalizer.bias'): W[k] = torch.randn(128, generator=g) * 0.1
     parts = [p.double() for p in _split_blob(pack_weights(W))]
     loc_emb, init_w, init_b = parts[0].view(92, 128), parts[1].view(3, 128), parts[2]
+    for l in range(3):          # K-major copies used by the tcgen05 GEMMs are exact transposes
+        assert torch.equal(parts[38 + 4 * l].view(384, 128), parts[3 + 10 * l].view(128, 384).t())
+        assert torch.equal(parts[39 + 4 * l].view(128, 128), parts[4 + 10 * l].view(128, 128).t())
+        assert torch.equal(parts[40 + 4 * l].view(512, 128), parts[7 + 10 * l].view(128, 512).t())
+        assert torch.equal(parts[41 + 4 * l].view(128, 512), parts[9 + 10 * l].view(512, 128).t())
+    assert torch.equal(parts[50].view(512, 128), parts[33].view(128, 512).t())
     inst = {k: v[:6] for k, v in make_instances(20).items()}
     task = O.fleet_task(tables, inst, 3, O.new_tw_left_levels(inst))
     B, N = task['loc'].shape
