@@ -83,6 +83,8 @@ def rollout(model, dataset, opts):
     model.eval()
     inner = get_inner_model(model)
     rank, ws = parallel.world()
+    if not getattr(opts, 'shard_across_ranks', True):     # every rank owns its whole dataset (weak-scaling benchmarks)
+        rank, ws = 0, 1
     lo, hi = parallel.shard_bounds(len(dataset), rank, ws)
     defer, inner.defer_checks = inner.defer_checks, True      # tour validity is asserted once per batch
     out = []

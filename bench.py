@@ -190,7 +190,8 @@ def run_cuda(args):
             if ev: events.append(ev)
         return torch.stack(costs, 1), torch.stack(inst_steps), status
 
-    opts = types.SimpleNamespace(eval_batch_size=B, device=dev, no_progress_bar=True)
+    # weak scaling: every rank rolls out its OWN batch through the public API (no cross-rank sharding of it)
+    opts = types.SimpleNamespace(eval_batch_size=B, device=dev, no_progress_bar=True, shard_across_ranks=False)
 
     for _ in range(args.warmup):
         step_resident()

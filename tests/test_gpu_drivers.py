@@ -1,0 +1,137 @@
+"""GPU tests of the reference's driver-level entry points: _eval_dataset (greedy and sampling),
+RolloutBaseline, train_batch_agh / train_epoch, load_model on a reference-format checkpoint directory."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, make_instances
+
+pytestmark = pytest.mark.gpu
+
+ARGS_JSON = {  # the fields of CB/data/<N>/args.json that load_model reads
+    'problem': 'agh', 'graph_size': 20, 'model': 'attention', 'embedding_dim': 128, 'hidden_dim': 128,
+    'n_encode_layers': 3, 'tanh_clipping': 10.0, 'normalization': 'batch', 'checkpoint_encoder': False,
+    'shrink_size': None, 'data_distribution': None, 'wo_time': False, 'rnn_time': False}
+
+
+def _dataset(n, size):
+    from agh_b200 import AGHDataset
+    ds = AGHDataset.__new__(AGHDataset)
+    torch.utils.data.Dataset.__init__(ds)
+    ds.arrays = {k: v[:size] for k, v in make_instances(n).items()}
+    ds.size = size
+    return ds
+
+
+def _eval_opts(**kw):
+    o = types.SimpleNamespace(decode_strategy='greedy', eval_batch_size=1000, max_calc_batch_size=10000,
+                              no_progress_bar=True, problem='agh', compress_mask=False)
+    o.__dict__.update(kw)
+    return o
+
+
+def test_load_model_and_eval_dataset_greedy(tmp_path, weights):
+    """eval.py path (config C1): a reference-format checkpoint dir (args.json + epoch-0.pt) loads and the greedy
+    evaluation of the seed-4321 AGH-20 set reproduces the reference's average cost."""
+    from agh_b200.utils import load_model
+    from agh_b200.eval import _eval_dataset
+    json.dump(ARGS_JSON, open(tmp_path / 'args.json', 'w'))
+    torch.save({'model': weights}, tmp_path / 'epoch-0.pt')
+    model, args = load_model(str(tmp_path))
+    assert args['problem'] == 'agh' and not model.training
+    res = _eval_dataset(model, _dataset(20, 1000), 0, 1.0, _eval_opts(), torch.device('cuda'))
+    g = load_golden('greedy_agh20.npz')
+    assert res.shape == (1000,) and res.dtype == torch.float32 and res.device.type == 'cpu'
+    ref = g['costs'].sum(1)
+    assert np.isclose(res.numpy(), ref, rtol=1e-5).mean() > 0.9
+    assert abs(res.mean().item() - float(g['avg'])) / float(g['avg']) < 2e-3
+
+
+def test_eval_dataset_sampling_best_of_width(cuda_model):
+    """Config C2 semantics: best of `width` samples per instance and fleet is never worse than the first sample, and
+    width 1280 with eval_batch_size 1 goes through the batch_rep / iter_rep split of eval.py:124-133."""
+    from agh_b200.eval import _eval_dataset
+    ds = _dataset(20, 6)
+    torch.manual_seed(5)
+    one = _eval_dataset(cuda_model, ds, 1, 1.0, _eval_opts(decode_strategy='sample', eval_batch_size=6), torch.device('cuda'))
+    torch.manual_seed(5)
+    many = _eval_dataset(cuda_model, ds, 64, 1.0, _eval_opts(decode_strategy='sample', eval_batch_size=6), torch.device('cuda'))
+    greedy = _eval_dataset(cuda_model, ds, 0, 1.0, _eval_opts(), torch.device('cuda'))
+    assert many.mean() < one.mean() and many.mean() < greedy.mean()
+    torch.manual_seed(5)
+    big = _eval_dataset(cuda_model, _dataset(20, 2), 1280, 1.0,
+                        _eval_opts(decode_strategy='sample', eval_batch_size=1, max_calc_batch_size=640), torch.device('cuda'))
+    assert big.shape == (2,) and (big < greedy[:2]).all()
+    torch.manual_seed(5)
+    again = _eval_dataset(cuda_model, _dataset(20, 2), 1280, 1.0,
+                          _eval_opts(decode_strategy='sample', eval_batch_size=1, max_calc_batch_size=640), torch.device('cuda'))
+    assert torch.equal(big, again)                       # reproducible under torch.manual_seed
+    cuda_model.set_decode_type('greedy')
+
+
+def _train_opts(tmp_path, **kw):
+    o = types.SimpleNamespace(eval_batch_size=64, device=torch.device('cuda'), no_progress_bar=True, max_grad_norm=1.0,
+                              log_step=1, no_tensorboard=True, baseline='rollout', save_dir=str(tmp_path),
+                              checkpoint_epochs=1, n_epochs=1, epoch_size=64, batch_size=32, graph_size=20,
+                              data_distribution=None, val_size=32, bl_alpha=0.05, run_name='test')
+    o.__dict__.update(kw)
+    return o
+
+
+def test_rollout_baseline_and_train_epoch(tmp_path, capsys):
+    """a17-a19: RolloutBaseline (wrap_dataset / unwrap_batch / epoch_callback / state_dict) and one train_epoch
+    (2 REINFORCE steps, checkpoint, validation) run end to end; parameters move and BatchNorm statistics update."""
+    from agh_b200 import AttentionModel, AGH
+    from agh_b200.reinforce_baselines import RolloutBaseline
+    from agh_b200.train import train_epoch, validate
+    torch.manual_seed(1234)
+    np.random.seed(7)
+    model = AttentionModel(128, 128, AGH).cuda()
+    opts = _train_opts(tmp_path)
+    baseline = RolloutBaseline(model, AGH, opts)
+    assert baseline.bl_vals.shape == (32,) and np.isfinite(baseline.mean)
+    wrapped = baseline.wrap_dataset(AGH.make_dataset(size=20, num_samples=8))
+    item = wrapped[3]
+    assert item['baseline'].shape == (10,) and item['data']['demand'].shape == (10, 20)
+    optimizer = torch.optim.Adam([{'params': model.parameters(), 'lr': 1e-4}])
+    sched = torch.optim.lr_scheduler.LambdaLR(optimizer, lambda e: 1.0)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    val = AGH.make_dataset(size=20, num_samples=32)
+    train_epoch(model, optimizer, baseline, sched, 0, val, AGH, None, opts)
+    out = capsys.readouterr().out
+    assert 'Finished epoch 0' in out and 'Validation overall avg_cost' in out and 'grad norm' in out
+    after = model.state_dict()
+    assert not torch.equal(before['project_out.weight'], after['project_out.weight'])
+    assert int(after['embedder.layers.2.3.normalizer.num_batches_tracked']) == 20      # 2 batches x 10 fleets
+    ck = torch.load(os.path.join(str(tmp_path), 'epoch-0.pt'), weights_only=False)
+    assert set(ck) == {'model', 'optimizer', 'rng_state', 'cuda_rng_state', 'baseline'}
+    assert set(ck['baseline']) == {'model', 'dataset', 'epoch'}
+    # resume: the saved baseline restores into a fresh RolloutBaseline
+    b2 = RolloutBaseline(model, AGH, opts)
+    b2.load_state_dict(ck['baseline'])
+    assert b2.epoch == 0 and len(b2.dataset) == 32
+    v = validate(model, val, opts)
+    assert torch.isfinite(v)
+
+
+def test_forward_accepts_the_reference_input_dict(cuda_model, tables):
+    """model(input) with the dict train.py:53-57 builds (f64 duration/tw_right, stride-0 distance, i64 fleet)."""
+    from oracle import agh_oracle as O
+    inst = {k: v[:32] for k, v in make_instances(20).items()}
+    g = load_golden('greedy_agh20.npz')
+    task = O.fleet_task(tables, inst, 1, O.new_tw_left_levels(inst))
+    assert task['distance'].stride(0) == 0 and task['duration'].dtype == torch.float64
+    cuda_model.set_decode_type('greedy')
+    with torch.no_grad():
+        cost, ll, serve, pi = cuda_model({k: v.cuda() for k, v in task.items()}, return_pi=True)
+    assert cost.dtype == ll.dtype == serve.dtype == torch.float32 and pi.dtype == torch.int64
+    assert serve.shape == (32, 21) and pi.shape[0] == 32 and cost.is_cuda
+    assert np.isclose(cost.cpu().numpy(), g['costs'][:32, 0], rtol=1e-5).mean() > 0.9
+    same = np.isclose(cost.cpu().numpy(), g['costs'][:32, 0], rtol=1e-5)
+    assert np.allclose(ll.cpu().numpy()[same], g['ll'][:32, 0][same], rtol=1e-4, atol=1e-4)
+    T = pi.shape[1]
+    assert np.array_equal(pi.cpu().numpy()[same], g['pi'][:32, 0, :T].astype(np.int64)[same])
