@@ -108,8 +108,8 @@ __host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int res
   s.twr = take(npad * 8); s.dur = take(npad * 8);
   s.twl = take(npad * 4); s.dem = take(npad * 4); s.crd = take(npad * 4);
   s.dcur = take(2 * npad * 4); s.z = take(npad * 4); s.serve = take(npad * 4);
-  s.o = take(D * 4); s.qb = take(D * 4); s.wc = take(D * 4); s.wt = take(D * 4);
-  s.red = take(8 * 8 * 4);
+  s.o = take(D * 4); s.qb = take(D * 4); s.wc = 0; s.wt = 0;       // qb slot holds the step's query vector
+  s.red = take(8 * 4 * 4);
   s.mw = take(16 * 4);
   s.bar = take(16);
   s.total = off;
@@ -148,9 +148,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   float* s_z = reinterpret_cast<float*>(smem + L.z);
   float* s_serve = reinterpret_cast<float*>(smem + L.serve);
   float* s_o = reinterpret_cast<float*>(smem + L.o);
-  float* s_qb = reinterpret_cast<float*>(smem + L.qb);
-  float* s_wc = reinterpret_cast<float*>(smem + L.wc);
-  float* s_wt = reinterpret_cast<float*>(smem + L.wt);
+  float* s_q = reinterpret_cast<float*>(smem + L.qb);        // query of the current step, written by threads 0..127
   float* s_red = reinterpret_cast<float*>(smem + L.red);
   uint32_t* s_mw = reinterpret_cast<uint32_t*>(smem + L.mw);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
@@ -197,10 +195,12 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     s_crd[j] = ok ? (int)a.coord[(size_t)kb * n + j] : 0;
     s_serve[j] = 0.f;
   }
+  // threads 0..127 each own one component of the query: base, capacity and time coefficients in registers
+  float qb_r = 0.f, wc_r = 0.f, wt_r = 0.f;
   if (tid < D) {
-    s_qb[tid] = a.qbase[(size_t)kb * D + tid];
-    s_wc[tid] = a.wblob[W_CAP + tid];
-    s_wt[tid] = a.wblob[W_TIME + tid];
+    qb_r = a.qbase[(size_t)kb * D + tid];
+    wc_r = a.wblob[W_CAP + tid];
+    wt_r = a.wblob[W_TIME + tid];
   }
   __syncthreads();
   mbar_wait(bar, 0);
@@ -256,31 +256,10 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       const double q0 = cft * inv;
       tf = (float)fma(fma(-q0, 1440.0, cft), inv, q0);
     }
-    // (3) compatibilities of my nodes with head h against the register-resident K' (which already holds
-    //     the 1/sqrt(16)); q is consumed chunk by chunk and never kept
-    float s[NPL];
-#pragma unroll
-    for (int p = 0; p < NPL; ++p) s[p] = 0.f;
-    {
-      const float4* pr = reinterpret_cast<const float4*>(Pm + (size_t)prev * D + h * HD);
-      const float4* qb4 = reinterpret_cast<const float4*>(s_qb + h * HD);
-      const float4* wc4 = reinterpret_cast<const float4*>(s_wc + h * HD);
-      const float4* wt4 = reinterpret_cast<const float4*>(s_wt + h * HD);
-      float4 pv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) pv[i] = (RES & RES_P) ? pr[i] : __ldg(pr + i);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 bv = qb4[i], cv = wc4[i], tv = wt4[i];
-        float4 qv;
-        qv.x = fmaf(tv.x, tf, fmaf(cv.x, rem, bv.x + pv[i].x));
-        qv.y = fmaf(tv.y, tf, fmaf(cv.y, rem, bv.y + pv[i].y));
-        qv.z = fmaf(tv.z, tf, fmaf(cv.z, rem, bv.z + pv[i].z));
-        qv.w = fmaf(tv.w, tf, fmaf(cv.w, rem, bv.w + pv[i].w));
-#pragma unroll
-        for (int p = 0; p < NPL; ++p)
-          s[p] = dot4(qv, make_float4(kreg[p][4 * i], kreg[p][4 * i + 1], kreg[p][4 * i + 2], kreg[p][4 * i + 3]), s[p]);
-      }
+    // one component of the query per thread (threads 0..127), published through shared memory
+    if (tid < D) {
+      const float pv = (RES & RES_P) ? Pm[(size_t)prev * D + tid] : __ldg(Pm + (size_t)prev * D + tid);
+      s_q[tid] = fmaf(wt_r, tf, fmaf(wc_r, rem, qb_r + pv));
     }
 
     // (4) feasibility of node tid (+256k): state_agh.py:148-174, exact dtypes; one node per thread, the
@@ -319,6 +298,22 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       }
     }
 
+    // (3) compatibilities of my nodes with head h against the register-resident K' (which already holds the
+    //     1/sqrt(16) and a log2(e), so the softmax below is exp2)
+    float s[NPL];
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) s[p] = 0.f;
+    {
+      const float4* q4 = reinterpret_cast<const float4*>(s_q + h * HD);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 qv = q4[i];
+#pragma unroll
+        for (int p = 0; p < NPL; ++p)
+          s[p] = dot4(qv, make_float4(kreg[p][4 * i], kreg[p][4 * i + 1], kreg[p][4 * i + 2], kreg[p][4 * i + 3]), s[p]);
+      }
+    }
+
     // (5) masked softmax over the nodes, warp-local: attention_model.py:559-565
     float mx = -CUDART_INF_F;
 #pragma unroll
@@ -331,7 +326,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     float e[NPL], esum = 0.f;
 #pragma unroll
     for (int p = 0; p < NPL; ++p) {
-      e[p] = expf(s[p] - mx);            // exp(-inf) = 0 for masked nodes; mx is finite (some node is feasible)
+      e[p] = exp2f(s[p] - mx);           // exp2(-inf) = 0 for masked nodes; mx is finite (some node is feasible)
       esum += e[p];
     }
 #pragma unroll
@@ -388,7 +383,8 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     const int half = lane >> 4, jj = lane & 15;
     constexpr int NPASS = (NPL * 32 + 127) / 128;
     float zp[NPASS];
-    float best_sc = -CUDART_INF_F, best_z = 0.f;
+    // selection score as an order-preserving integer key, so the arg-max is two warp REDUX operations
+    int best_key = (int)0x80000000;
     int best_j = 0x7fffffff;
 #pragma unroll
     for (int ps = 0; ps < NPASS; ++ps) {
@@ -422,7 +418,9 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
       }
       zp[ps] = (half == 0) ? z : -CUDART_INF_F;
-      if (half == 0 && sc > best_sc) { best_sc = sc; best_j = j; best_z = z; }
+      int key = __float_as_int(sc);
+      key ^= (key >> 31) & 0x7fffffff;                          // monotone float -> int map
+      if (half == 0 && key > best_key) { best_key = key; best_j = j; }     // strict: first index wins ties
     }
     float wm = shift, ws = 0.f;
     if (!fixed_shift) {
@@ -435,52 +433,40 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
 #pragma unroll
     for (int ps = 0; ps < NPASS; ++ps) ws += (zp[ps] == -CUDART_INF_F) ? 0.f : expf(zp[ps] - wm);
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      ws += __shfl_xor_sync(0xffffffffu, ws, off);
-      const float osc = __shfl_xor_sync(0xffffffffu, best_sc, off);
-      const int oj = __shfl_xor_sync(0xffffffffu, best_j, off);
-      const float oz = __shfl_xor_sync(0xffffffffu, best_z, off);
-      if (osc > best_sc || (osc == best_sc && oj < best_j)) { best_sc = osc; best_j = oj; best_z = oz; }
-    }
-    if (lane == 0) {
-      float4* r = reinterpret_cast<float4*>(s_red + warp * 8);
-      r[0] = make_float4(ws, best_sc, __int_as_float(best_j), best_z);
-      r[1] = make_float4(wm, 0.f, 0.f, 0.f);
+    for (int off = 16; off >= 1; off >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, off);
+    {
+      const int kmax = __reduce_max_sync(0xffffffffu, best_key);
+      const int jmin = __reduce_min_sync(0xffffffffu, best_key == kmax ? best_j : 0x7fffffff);
+      if (lane == 0)
+        *reinterpret_cast<float4*>(s_red + warp * 4) = make_float4(ws, __int_as_float(kmax), __int_as_float(jmin), wm);
     }
     __syncthreads();   // (B) per-warp partials complete
 
-    // (8) merge, select, update (every thread, redundantly): attention_model.py:446-447,372-390; state_agh.py:99-137
-    float M = shift, S = 0.f;
-    float g_sc = -CUDART_INF_F, g_z = 0.f;
-    int sel = 0x7fffffff;
-    if (fixed_shift) {
+    // (8) merge (lanes 0..7 take one warp's partial each), select, update; every warp does it redundantly so the
+    //     state stays in registers: attention_model.py:446-447,372-390; state_agh.py:99-137
+    float M = shift, S;
+    int sel;
+    {
+      float4 pr = make_float4(0.f, __int_as_float((int)0x80000000), __int_as_float(0x7fffffff), -CUDART_INF_F);
+      if (lane < 8) pr = *reinterpret_cast<const float4*>(s_red + lane * 4);
+      const int key = __float_as_int(pr.y);
+      const int kmax = __reduce_max_sync(0xffffffffu, key);
+      sel = __reduce_min_sync(0xffffffffu, key == kmax ? __float_as_int(pr.z) : 0x7fffffff);
+      float part = pr.x;
+      if (!fixed_shift) {
+        float wmax = pr.w;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const float4 r0 = reinterpret_cast<const float4*>(s_red + w * 8)[0];
-        S += r0.x;
-        const int oj = __float_as_int(r0.z);
-        if (r0.y > g_sc || (r0.y == g_sc && oj < sel)) { g_sc = r0.y; sel = oj; g_z = r0.w; }
-      }
-    } else {
-      float wms[8], wss[8];
-      M = -CUDART_INF_F;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const float4 r0 = reinterpret_cast<const float4*>(s_red + w * 8)[0];
-        wss[w] = r0.x;
-        wms[w] = s_red[w * 8 + 4];
-        M = fmaxf(M, wms[w]);
-        const int oj = __float_as_int(r0.z);
-        if (r0.y > g_sc || (r0.y == g_sc && oj < sel)) { g_sc = r0.y; sel = oj; g_z = r0.w; }
+        for (int off = 4; off >= 1; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+        M = __shfl_sync(0xffffffffu, wmax, 0);
+        part = (pr.w == -CUDART_INF_F) ? 0.f : pr.x * expf(pr.w - M);
       }
 #pragma unroll
-      for (int w = 0; w < 8; ++w) S += (wms[w] == -CUDART_INF_F) ? 0.f : wss[w] * expf(wms[w] - M);
+      for (int off = 4; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      S = __shfl_sync(0xffffffffu, part, 0);
     }
     const float logS = logf(S);
-    if (replay) {
-      sel = (int)a.actions[trow + t];
-      g_z = s_z[sel];
-    }
+    if (replay) sel = (int)a.actions[trow + t];
+    const float g_z = s_z[sel];
     const float lp = (g_z - M) - logS;
     ll += lp;
     if (a.logp_full != nullptr) {

@@ -49,7 +49,8 @@ def pack_weights(sd: Dict[str, torch.Tensor], device=None) -> torch.Tensor:
     wout = g('project_out.weight')                           # [128][128]  glimpse = W_out o
     wsc = g('project_step_context.weight')                   # [128][130]
     lk_fold = (wout.t() @ wn[2 * D:3 * D]) / math.sqrt(D)    # [c][e]
-    wdec = torch.cat((wn[0:D].t() / math.sqrt(D // H), wn[D:2 * D].t(), lk_fold.t(), wsc[:, :D].t()), 1)   # [128][512]
+    # K' carries 1/sqrt(16) and log2(e): the glimpse softmax runs in base 2 (exp2) in the kernel
+    wdec = torch.cat((wn[0:D].t() * (math.log2(math.e) / math.sqrt(D // H)), wn[D:2 * D].t(), lk_fold.t(), wsc[:, :D].t()), 1)   # [128][512]
     parts += [wdec, g('project_fixed_context.weight').t(), g('fleets_embedding.weight'), wsc[:, D], wsc[:, D + 1]]
     parts += tc_parts + [wdec.t()]
     blob = torch.cat([p.contiguous().reshape(-1) for p in parts]).to(torch.float32).contiguous()

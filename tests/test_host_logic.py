@@ -127,6 +127,7 @@ def test_weight_folds_reproduce_the_oracle(weights, tables):
     wdec, wfc_t, fleet_emb, w_cap, w_time = parts[33].view(128, 512), parts[34].view(128, 128), parts[35].view(10, 128), parts[36], parts[37]
     proj = h_ref.double() @ wdec
     Kp, V, Lp, Psc = proj.split(128, -1)
+    Kp = Kp / math.log2(math.e)          # the blob's K' is pre-scaled for the kernel's exp2 softmax
     qbase = h_ref.double().mean(1) @ wfc_t + fleet_emb[task['fleet'][:, 0]]
     rec = {}
     with torch.no_grad():
