@@ -179,58 +179,101 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // self-attention, one CTA per (instance, head): graph_encoder.py:83-104
 // ------------------------------------------------------------------------------------------
+// One CTA = two heads of one instance, 64 threads per head, TWO query rows per thread: every K_j / V_j row read
+// from shared memory (broadcast LDS.128) feeds two rows, which halves the shared-memory instruction stream that
+// otherwise ties with the FMAs.  Online softmax in base 2, four keys per iteration.
 __global__ void __launch_bounds__(128) mha_kernel(const float* __restrict__ qkv, int n, float* __restrict__ heads) {
   extern __shared__ __align__(16) float sm[];
-  float4* sKh = reinterpret_cast<float4*>(sm);               // [n][4] float4
+  const int b = blockIdx.x / (H / 2);
+  const int hl = threadIdx.x >> 6;                           // local head 0/1
+  const int h = (blockIdx.x % (H / 2)) * 2 + hl;
+  const int t = threadIdx.x & 63;
+  float4* sKh = reinterpret_cast<float4*>(sm) + (size_t)hl * n * 8;     // [n][4] float4 K, then [n][4] float4 V
   float4* sVh = sKh + (size_t)n * 4;
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
   const float* base = qkv + (size_t)b * n * (3 * D);
-  for (int idx = threadIdx.x; idx < n * 4; idx += blockDim.x) {
+  for (int idx = t; idx < n * 4; idx += 64) {
     const int j = idx >> 2, c = idx & 3;
     sKh[idx] = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * D + D + h * HD + c * 4);
     sVh[idx] = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * D + 2 * D + h * HD + c * 4);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float q[HD];
+  for (int i0 = t; i0 < n; i0 += 128) {
+    const int i1 = i0 + 64;
+    const bool has1 = i1 < n;
+    float q0[HD], q1[HD], o0[HD], o1[HD];
+    // norm_factor = 1/sqrt(16) (graph_encoder.py:40,89) and log2(e) go into q once: the softmax runs in base 2
+    const float qs = 0.25f * 1.4426950408889634f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)i * 3 * D + h * HD + c * 4);
-      q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
+      const float4 v0 = *reinterpret_cast<const float4*>(base + (size_t)i0 * 3 * D + h * HD + c * 4);
+      const float4 v1 = has1 ? *reinterpret_cast<const float4*>(base + (size_t)i1 * 3 * D + h * HD + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      q0[4 * c] = v0.x * qs; q0[4 * c + 1] = v0.y * qs; q0[4 * c + 2] = v0.z * qs; q0[4 * c + 3] = v0.w * qs;
+      q1[4 * c] = v1.x * qs; q1[4 * c + 1] = v1.y * qs; q1[4 * c + 2] = v1.z * qs; q1[4 * c + 3] = v1.w * qs;
     }
-    float m = -CUDART_INF_F, l = 0.f, o[HD];
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < HD; ++k) o[k] = 0.f;
-#pragma unroll 2
-    for (int j = 0; j < n; ++j) {
-      float s = 0.f;
+    for (int k = 0; k < HD; ++k) { o0[k] = 0.f; o1[k] = 0.f; }
+    auto score2 = [&](int j, float& s0, float& s1) {
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float4 kv = sKh[j * 4 + c];
-        s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s); s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
+        a0 = fmaf(q0[4 * c], kv.x, a0); a1 = fmaf(q0[4 * c + 1], kv.y, a1); a0 = fmaf(q0[4 * c + 2], kv.z, a0); a1 = fmaf(q0[4 * c + 3], kv.w, a1);
+        b0 = fmaf(q1[4 * c], kv.x, b0); b1 = fmaf(q1[4 * c + 1], kv.y, b1); b0 = fmaf(q1[4 * c + 2], kv.z, b0); b1 = fmaf(q1[4 * c + 3], kv.w, b1);
       }
-      s *= 0.25f;                                  // norm_factor = 1/sqrt(16), graph_encoder.py:40,89
-      if (s > m) {
-        const float c0 = expf(m - s);
-        l *= c0;
-#pragma unroll
-        for (int k = 0; k < HD; ++k) o[k] *= c0;
-        m = s;
-      }
-      const float p = expf(s - m);
-      l += p;
+      s0 = a0 + a1; s1 = b0 + b1;
+    };
+    auto accumulate2 = [&](int j, float p0, float p1) {
+      l0 += p0; l1 += p1;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float4 vv = sVh[j * 4 + c];
-        o[4 * c] = fmaf(p, vv.x, o[4 * c]); o[4 * c + 1] = fmaf(p, vv.y, o[4 * c + 1]);
-        o[4 * c + 2] = fmaf(p, vv.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(p, vv.w, o[4 * c + 3]);
+        o0[4 * c] = fmaf(p0, vv.x, o0[4 * c]); o0[4 * c + 1] = fmaf(p0, vv.y, o0[4 * c + 1]);
+        o0[4 * c + 2] = fmaf(p0, vv.z, o0[4 * c + 2]); o0[4 * c + 3] = fmaf(p0, vv.w, o0[4 * c + 3]);
+        o1[4 * c] = fmaf(p1, vv.x, o1[4 * c]); o1[4 * c + 1] = fmaf(p1, vv.y, o1[4 * c + 1]);
+        o1[4 * c + 2] = fmaf(p1, vv.z, o1[4 * c + 2]); o1[4 * c + 3] = fmaf(p1, vv.w, o1[4 * c + 3]);
       }
-    }
-    const float inv = 1.0f / l;
-    float* out = heads + ((size_t)b * n + i) * D + h * HD;
+    };
+    auto raise_max = [&](float cm, float& m, float& l, float (&o)[HD]) {   // rescale only when the running max rises
+      if (cm > m) {
+        const float c0 = exp2f(m - cm);
+        l *= c0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      *reinterpret_cast<float4*>(out + 4 * c) = make_float4(o[4 * c] * inv, o[4 * c + 1] * inv, o[4 * c + 2] * inv, o[4 * c + 3] * inv);
+        for (int k = 0; k < HD; ++k) o[k] *= c0;
+        m = cm;
+      }
+    };
+    int j = 0;
+    for (; j + 4 <= n; j += 4) {
+      float s0[4], s1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) score2(j + u, s0[u], s1[u]);
+      raise_max(fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s0[2], s0[3])), m0, l0, o0);
+      raise_max(fmaxf(fmaxf(s1[0], s1[1]), fmaxf(s1[2], s1[3])), m1, l1, o1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) accumulate2(j + u, exp2f(s0[u] - m0), exp2f(s1[u] - m1));
+    }
+    for (; j < n; ++j) {
+      float s0, s1;
+      score2(j, s0, s1);
+      raise_max(s0, m0, l0, o0);
+      raise_max(s1, m1, l1, o1);
+      accumulate2(j, exp2f(s0 - m0), exp2f(s1 - m1));
+    }
+    {
+      const float inv = 1.0f / l0;
+      float* out = heads + ((size_t)b * n + i0) * D + h * HD;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(out + 4 * c) = make_float4(o0[4 * c] * inv, o0[4 * c + 1] * inv, o0[4 * c + 2] * inv, o0[4 * c + 3] * inv);
+    }
+    if (has1) {
+      const float inv = 1.0f / l1;
+      float* out = heads + ((size_t)b * n + i1) * D + h * HD;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(out + 4 * c) = make_float4(o1[4 * c] * inv, o1[4 * c + 1] * inv, o1[4 * c + 2] * inv, o1[4 * c + 3] * inv);
+    }
   }
 }
 
@@ -294,8 +337,8 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
   float* hid = x1 + (size_t)M * D;
   float* xa = hid + (size_t)M * FF;
   const float* x = h0;
-  const int mha_threads = n >= 128 ? 128 : 32 * ceil_div(n, 32);
-  const size_t mha_smem = (size_t)n * 2 * HD * sizeof(float);
+  const int mha_threads = 128;                                     // 2 heads x 64 threads, 2 query rows per thread
+  const size_t mha_smem = (size_t)n * 4 * HD * sizeof(float);
   if (mha_smem > 48 * 1024) AGH_CUDA(cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mha_smem));
   for (int l = 0; l < LAYERS; ++l) {
     const float* lw = wblob + W_LAYER0 + (size_t)l * L_SIZE;
@@ -305,7 +348,7 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
     g.A = x; g.lda = D; g.W = lw + L_WQKV; g.Wt = tw + T_WQKV; g.C = qkv; g.ldc = 3 * D; g.M = M; g.K = D; g.Nc = 3 * D;
     int rc = launch_gemm<EPI_PLAIN>(g, st);
     if (rc) return rc;
-    mha_kernel<<<B * H, mha_threads, mha_smem, st>>>(qkv, n, heads);
+    mha_kernel<<<B * (H / 2), mha_threads, mha_smem, st>>>(qkv, n, heads);
     AGH_LAUNCH_CHECK();
     g = GemmArgs{};
     g.A = heads; g.lda = D; g.W = lw + L_WO; g.Wt = tw + T_WO; g.C = x1; g.ldc = D; g.M = M; g.K = D; g.Nc = D;
