@@ -151,6 +151,16 @@ struct Cfg {
   static constexpr int SMEM = WRES_BYTES + STAGES * STAGE_BYTES + 1024 /*align*/ + 8 * NBARS + 16;
 };
 
+// Which epilogues go through the in-register 32x32 transpose (coalesced 128-byte rows) instead of the row-wise
+// 16-byte accesses: bit EPI of the mask.  Overridable at compile time for A/B measurements.  Measured per launch at
+// M = 1.01 M rows (transposed vs row-wise): QKV/plain 688 vs 1010 us, out-proj 615 vs 636, FF2 1070 vs 1260 (both
+// residual+BN, with the residual prefetched), FF1/bias+ReLU 2215 vs 1560, key scatter 2750 vs 1150 -> plain and
+// residual+BN epilogues are transposed, the two 512-column outputs stay row-wise.
+#ifndef AGH_TC_TRANSPOSE_MASK
+#define AGH_TC_TRANSPOSE_MASK 0x5
+#endif
+__host__ __device__ constexpr bool epi_transposed(int epi) { return (AGH_TC_TRANSPOSE_MASK >> epi) & 1; }
+
 template <int EPI, bool WRES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
@@ -284,10 +294,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t tile = 0;
     for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++tile) {
       const int ab = tile % C::NBUF;
+      const int row0 = mt * BM + q * 32;
+      // transposed domain: lane = column, rr[i] = residual of row row0 + i.  The residual does not depend on the
+      // MMAs, so its (coalesced) loads are issued BEFORE waiting for the accumulator and one chunk ahead after that.
+      float rr[32];
+      auto load_res = [&](int c0, float (&dst)[32]) {
+        const float* src = g.res + (size_t)row0 * g.ldr + n0 + c0 + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[i] = (row0 + i < g.M) ? __ldg(src + (size_t)i * g.ldr) : 0.f;
+      };
+      if (EPI == EPI_RES_BN && epi_transposed(EPI)) load_res(0, rr);
       mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t t_acc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
-      const int row0 = mt * BM + q * 32;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float r[32];
@@ -309,9 +328,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty(ab));
         }
-        if (EPI != EPI_PLAIN) {
+        if (!epi_transposed(EPI)) {
           // row-wise epilogue: this thread owns row `row0 + lane`, 8 x 16-byte accesses per 32-column chunk
-          // (measured faster than the transposed variant below whenever the epilogue reads bias / residual / BN)
           const int row = row0 + lane;
           if (row >= g.M) continue;
           int bi = 0, j = 0;
@@ -368,20 +386,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (EPI == EPI_RES_BN) { sc = g.bn_s[col]; sh = g.bn_t[col]; }
         int mat = 0, cc = 0, bi = 0, j = 0;
         if (EPI == EPI_DEC) { mat = col / D; cc = col % D; bi = row0 / g.n; j = row0 % g.n; }
-        float rr[32];
-        if (EPI == EPI_RES_BN) {          // all residual loads first: 32 independent coalesced 128-byte reads in flight
+        if (EPI == EPI_RES_BN) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) rr[i] = (row0 + i < g.M) ? __ldg(g.res + (size_t)(row0 + i) * g.ldr + col) : 0.f;
+          for (int i = 0; i < 32; ++i) r[i] = fmaf(rr[i] + (r[i] + bias), sc, sh);
+          if (c0 + 32 < BN) load_res(c0 + 32, rr);        // next chunk's residual flies while this chunk is stored
         }
 #pragma unroll      // full unroll: r[] must stay in registers (static indices only)
         for (int i = 0; i < 32; ++i) {
           const int row = row0 + i;
           float v = r[i];
-          if (EPI == EPI_BIAS_RELU) {
-            v = fmaxf(v + bias, 0.f);
-          } else if (EPI == EPI_RES_BN) {
-            v = fmaf(rr[i] + (v + bias), sc, sh);
-          }
+          if (EPI == EPI_BIAS_RELU) v = fmaxf(v + bias, 0.f);
           if (row < g.M) {
             if (EPI == EPI_DEC) {
               if (mat < 3) {
