@@ -242,6 +242,11 @@ def run_cuda(args):
         achieved = a_step_bytes(N) * inst_steps_per_launch / (dec_launch_ms * 1e-3) / 1e9
         enc_tflops = f_enc_flops(N) * B * 10 / ((t_enc + t_pre) * 1e-3) / 1e12
         h2d = sum(v.numel() * v.element_size() for v in host.values())
+        # physical DRAM bytes per decode launch from the committed `ncu --set full` capture of this very workload
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'r1d_decode_traffic.json')
+        if os.path.exists(tp) and (N, B) == (100, 10000):
+            traffic = json.load(open(tp))['traffic_bytes_per_launch']
         line = {
             'metric': METRIC, 'value': B * ws / (ms_res * 1e-3), 'unit': UNIT, 'n_gpus': ws, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -256,16 +261,18 @@ def run_cuda(args):
                     'ms_per_step': ms_e2e, 'api': 'agh_b200.train.rollout(model, dataset, opts)'},
             'gpu_launches': int(launches),
             'roofline': {'kernel': 'decode_kernel (agh_decode)', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm,
-                         'unit': 'GB/s', 'frac': achieved / hbm, 'traffic': None, 'peak_source': which,
+                         'unit': 'GB/s', 'frac': achieved / hbm, 'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read+write)',
+                         'peak_source': which, 'algorithmic_bytes_per_launch': a_step_bytes(N) * inst_steps_per_launch,
                          'algorithmic_bytes_per_instance_step': a_step_bytes(N),
                          'instance_steps_per_launch': inst_steps_per_launch, 'launch_ms': dec_launch_ms,
                          'share_of_step': t_dec / ms_res,
-                         'note': 'keys stay in shared memory across steps, so the effective fraction may exceed 1; '
-                                 'physical DRAM bytes are in profiles/'},
-            'roofline_encoder': {'kernels': 'sgemm_kernel + mha_kernel + init_embed (agh_encode, agh_precompute)',
+                         'note': 'keys stay on chip (registers + shared memory) for all T steps, so the fraction exceeds 1: '
+                                 'physical DRAM traffic is the one-time staging only (profiles/r1d_decode_traffic.json)'},
+            'roofline_encoder': {'kernels': 'gemm_tc_kernel + mha_kernel + init_embed (agh_encode, agh_precompute)',
                                  'bound': 'tensor', 'achieved': enc_tflops, 'peak': tflops, 'unit': 'TFLOP/s',
                                  'frac': enc_tflops / tflops, 'share_of_step': (t_enc + t_pre) / ms_res,
-                                 'note': 'fp32 CUDA-core path this round; peak is the measured bf16 cuBLAS figure'},
+                                 'note': 'tcgen05 kind::tf32 with the 3xTF32 split (3 MMAs per product) + CUDA-core attention; '
+                                         'achieved counts algorithmic fp32 flops, peak is the measured bf16 cuBLAS figure'},
             'phase_ms': {'encode': t_enc, 'precompute': t_pre, 'decode': t_dec},
             'decode_instance_steps_per_sec': total_inst_steps * ws / (ms_res * 1e-3),
             'avg_cost': float(host_costs.sum(1).mean()),
