@@ -135,3 +135,24 @@ def test_forward_accepts_the_reference_input_dict(cuda_model, tables):
     assert np.allclose(ll.cpu().numpy()[same], g['ll'][:32, 0][same], rtol=1e-4, atol=1e-4)
     T = pi.shape[1]
     assert np.array_equal(pi.cpu().numpy()[same], g['pi'][:32, 0, :T].astype(np.int64)[same])
+
+
+def test_run_cli_train_and_resume(tmp_path, capsys):
+    """run.py path: two tiny epochs, then --resume from the first checkpoint continues at epoch 1."""
+    from agh_b200.options import get_options
+    from agh_b200.run import run
+    common = ['--graph_size', '20', '--epoch_size', '32', '--batch_size', '16', '--val_size', '16', '--eval_batch_size', '16',
+              '--output_dir', str(tmp_path), '--run_name', 't']
+    opts = get_options(common + ['--n_epochs', '1'])
+    run(opts)
+    ck = os.path.join(opts.save_dir, 'epoch-0.pt')
+    assert os.path.exists(ck) and os.path.exists(os.path.join(opts.save_dir, 'args.json'))
+    saved = json.load(open(os.path.join(opts.save_dir, 'args.json')))
+    assert saved['problem'] == 'agh' and saved['graph_size'] == 20 and saved['wo_time'] is False
+    opts2 = get_options(common + ['--n_epochs', '1', '--resume', ck])
+    run(opts2)
+    out = capsys.readouterr().out
+    assert 'Resuming after 0' in out and 'Start train epoch 1' in out
+    from agh_b200.utils import load_model
+    model, args = load_model(opts.save_dir)            # the run directory is a loadable model directory
+    assert args['graph_size'] == 20 and model.is_agh

@@ -252,3 +252,23 @@ def test_shard_bounds_cover_everything():
             b = [shard_bounds(n, r, ws) for r in range(ws)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
             assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def test_options_match_reference_flags():
+    """Every key of the reference's args.json (CB/data/100/args.json) is produced by get_options with the same default."""
+    from agh_b200.options import get_options
+    ref = {"problem": "agh", "graph_size": 100, "batch_size": 64, "epoch_size": 12800, "val_size": 1000, "val_dataset": None,
+           "model": "attention", "embedding_dim": 128, "hidden_dim": 128, "n_encode_layers": 3, "tanh_clipping": 10.0,
+           "normalization": "batch", "optimizer": "Adam", "lr_model": 0.0001, "lr_critic": 0.0001, "lr_decay": 1.0,
+           "eval_only": False, "n_epochs": 100, "seed": 1234, "max_grad_norm": 1.0, "no_cuda": False, "exp_beta": 0.8,
+           "baseline": "rollout", "bl_alpha": 0.05, "bl_warmup_epochs": 0, "eval_batch_size": 1000,
+           "checkpoint_encoder": False, "shrink_size": None, "data_distribution": None, "log_step": 50, "log_dir": "logs",
+           "output_dir": "outputs", "epoch_start": 0, "checkpoint_epochs": 1, "load_path": None, "resume": None,
+           "no_tensorboard": True, "no_progress_bar": True, "fine_tune": False, "wo_time": False, "rnn_time": False,
+           "log_stdout": True}
+    o = vars(get_options(['--graph_size', '100']))
+    for k, v in ref.items():
+        assert k in o and o[k] == v, k
+    assert o['save_dir'].startswith(os.path.join('outputs', 'agh_100', 'run_'))
+    with pytest.raises(AssertionError):
+        get_options(['--epoch_size', '100', '--batch_size', '64'])
