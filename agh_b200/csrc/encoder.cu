@@ -348,8 +348,14 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
     g.A = x; g.lda = D; g.W = lw + L_WQKV; g.Wt = tw + T_WQKV; g.C = qkv; g.ldc = 3 * D; g.M = M; g.K = D; g.Nc = 3 * D;
     int rc = launch_gemm<EPI_PLAIN>(g, st);
     if (rc) return rc;
-    mha_kernel<<<B * (H / 2), mha_threads, mha_smem, st>>>(qkv, n, heads);
-    AGH_LAUNCH_CHECK();
+    static const bool mha_simt = getenv("AGH_MHA") != nullptr && strcmp(getenv("AGH_MHA"), "simt") == 0;
+    if (use_tensor_cores() && !mha_simt) {
+      rc = launch_mha_mma(qkv, B, n, heads, st);
+      if (rc) return rc;
+    } else {
+      mha_kernel<<<B * (H / 2), mha_threads, mha_smem, st>>>(qkv, n, heads);
+      AGH_LAUNCH_CHECK();
+    }
     g = GemmArgs{};
     g.A = heads; g.lda = D; g.W = lw + L_WO; g.Wt = tw + T_WO; g.C = x1; g.ldc = D; g.M = M; g.K = D; g.Nc = D;
     g.res = x; g.ldr = D; g.bn_s = lw + L_BN1S; g.bn_t = lw + L_BN1T;

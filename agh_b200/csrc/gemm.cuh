@@ -22,4 +22,7 @@ struct GemmArgs {
 template <int EPI>
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 
+// Self-attention of all heads on mma.sync tensor cores (mha_mma.cu): qkv [B*n][384] -> heads [B*n][128].
+int launch_mha_mma(const float* qkv, int B, int n, float* heads, cudaStream_t st);
+
 }  // namespace agh
