@@ -9,11 +9,14 @@
 // are issued first so the small terms enter the accumulator before the large ones; for O (a sum over all keys) they
 // have their own accumulator so that they are not absorbed by the growing partial sums.
 //
-// Shared memory holds K_h and V_h of the CTA's heads already split, as (hi, lo) pairs, so the inner loop has no
-// conversion work for them and every fragment element is one LDS.64.  Row strides of 20 (K) and 18 (V) pairs make
-// both fragment access patterns bank-conflict free.  The P fragments of the second product are the score
-// fragments themselves: a thread's score columns (2t, 2t+1) are fed as A-columns (t, t+4), and the V fragment is
-// loaded with rows (2t, 2t+1) to match, so no shuffle is needed between the two products.
+// One CTA walks the heads of one instance.  The raw Q_h|K_h|V_h rows of the NEXT head stream into shared memory
+// with cp.async while the warps work on the current one, so the global-memory latency is paid once per instance.
+// A short pass then rewrites K_h and V_h as TF32 (hi, lo) values in fragment order: the two B-fragment registers
+// of every mma are adjacent in shared memory (K: columns t and t+4 of one key; V: keys 2t and 2t+1 of one column),
+// so each fragment is ONE LDS.64 straight into the register pair the instruction needs.  Row strides (20 and 36
+// pairs) keep those loads bank-conflict free.  The P fragments of the second product are the score fragments
+// themselves: a thread's score columns (2t, 2t+1) are fed as A-columns (t, t+4) and the V pairs follow the same
+// key order, so no shuffle is needed between the two products.
 #include "common.cuh"
 #include "gemm.cuh"
 #include <math_constants.h>
@@ -23,12 +26,10 @@ namespace agh {
 
 namespace {
 
-constexpr int KSTR = 20;          // K row stride, in (hi, lo) pairs
-constexpr int VSTR = 18;          // V row stride, in (hi, lo) pairs
+constexpr int RAWS = 52;          // raw row stride in floats: Q 16 | K 16 | V 16 | pad 4
+constexpr int KSTR = 20;          // split K row (one key): 8 hi pairs, 8 lo pairs, 4 pad
+constexpr int VSTR = 36;          // split V row (two keys): 16 hi pairs, 16 lo pairs, 4 pad
 constexpr int MHA_MAX_THREADS = 640;
-#ifndef MHA_MINB_SMALL
-#define MHA_MINB_SMALL 2
-#endif
 
 __device__ __forceinline__ uint32_t tf32_rn(float x) {          // round to nearest TF32 (ties away), finite inputs
   return (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
@@ -37,190 +38,199 @@ __device__ __forceinline__ void split_rn(float x, uint32_t& hi, uint32_t& lo) {
   hi = tf32_rn(x);
   lo = tf32_rn(x - __uint_as_float(hi));
 }
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void stage_row(float2* dst, const float4 v) {       // 4 values -> 4 (hi, lo) pairs
-  uint32_t hi[4], lo[4];
-  split_rn(v.x, hi[0], lo[0]); split_rn(v.y, hi[1], lo[1]); split_rn(v.z, hi[2], lo[2]); split_rn(v.w, hi[3], lo[3]);
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+// (a_i, b_i), i = 0..3  ->  4 hi pairs at dst[0..3], 4 lo pairs at dst[lo_off..lo_off+3]
+__device__ __forceinline__ void store_pairs(uint2* dst, int lo_off, const float4 a, const float4 b) {
+  uint32_t ah[4], al[4], bh[4], bl[4];
+  split_rn(a.x, ah[0], al[0]); split_rn(a.y, ah[1], al[1]); split_rn(a.z, ah[2], al[2]); split_rn(a.w, ah[3], al[3]);
+  split_rn(b.x, bh[0], bl[0]); split_rn(b.y, bh[1], bl[1]); split_rn(b.z, bh[2], bl[2]); split_rn(b.w, bh[3], bl[3]);
   uint4* d = reinterpret_cast<uint4*>(dst);
-  d[0] = make_uint4(hi[0], lo[0], hi[1], lo[1]);
-  d[1] = make_uint4(hi[2], lo[2], hi[3], lo[3]);
+  d[0] = make_uint4(ah[0], bh[0], ah[1], bh[1]);
+  d[1] = make_uint4(ah[2], bh[2], ah[3], bh[3]);
+  uint4* e = reinterpret_cast<uint4*>(dst + lo_off);
+  e[0] = make_uint4(al[0], bl[0], al[1], bl[1]);
+  e[1] = make_uint4(al[2], bl[2], al[3], bl[3]);
 }
 
-// grid = B * (H / hpc) CTAs, block = hpc * mt warps: warp w works on head (w / mt) of the CTA and query rows
-// [16 (w % mt), 16 (w % mt) + 16).  CH = key fragments (8 keys each) per online-softmax chunk; the shared-memory
-// rows are zero-padded to whole chunks, so the chunk body is branch-free.
+__host__ __device__ inline size_t lane_bytes(int npad) {
+  return (size_t)npad * RAWS * 4 + (size_t)npad * KSTR * 8 + (size_t)(npad / 2) * VSTR * 8;
+}
+
+// grid = B CTAs, block = hpc * mt warps.  The CTA's warps form hpc "head lanes" of mt warps; lane hl walks heads
+// hl, hl + hpc, ... of the instance, warp (w % mt) of a lane owning query rows [16 (w % mt), +16).  CH = key
+// fragments (8 keys each) per online-softmax chunk; shared-memory rows are zero-padded to whole chunks, so the
+// chunk body is branch-free.
 template <int CH, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __restrict__ qkv, int n, int hpc, int mt,
-                                                                  float* __restrict__ heads) {
-  extern __shared__ __align__(16) float2 sm2[];
+                                                             float* __restrict__ heads) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nchunk = (n + 8 * CH - 1) / (8 * CH), npad = nchunk * 8 * CH;
-  const int groups = H / hpc;
-  const int b = blockIdx.x / groups;
-  const int h0 = (blockIdx.x % groups) * hpc;
+  const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const float* base = qkv + (size_t)b * n * (3 * D);
-  const int head_pairs = npad * (KSTR + VSTR);
-
-  // ---- Q fragments of this warp's 16 rows, straight from global memory (in flight during the staging below) ----
   const int hl = warp / mt, mi = warp - hl * mt;
-  const int h = h0 + hl;
+  const int lt = threadIdx.x - hl * mt * 32, lthreads = mt * 32;
+  const float* base = qkv + (size_t)b * n * (3 * D);
+  float* raw = reinterpret_cast<float*>(smem_raw + hl * lane_bytes(npad));
+  uint2* ksp = reinterpret_cast<uint2*>(raw + npad * RAWS);
+  uint2* vsp = ksp + npad * KSTR;
   const int r0 = mi * 16 + g, r1 = r0 + 8;
-  float qraw[2][4];
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int r = (e & 1) ? r1 : r0;
-      const int col = ks * 8 + t + ((e & 2) ? 4 : 0);
-      qraw[ks][e] = (r < n) ? __ldg(base + (size_t)r * 3 * D + h * HD + col) : 0.f;
-    }
-  }
+  const int nit = H / hpc;
 
-  // ---- stage K_h, V_h of the CTA's heads, split into (hi, lo); two rows in flight per thread ----
-  const int items = hpc * npad * 4;
-  for (int idx = threadIdx.x; idx < items; idx += 2 * blockDim.x) {
-    const int idx2 = idx + blockDim.x;
-    const int hla = idx / (npad * 4), ra = idx - hla * npad * 4;
-    const int hlb = idx2 / (npad * 4), rb = idx2 - hlb * npad * 4;
-    const int ja = ra >> 2, ca = ra & 3, jb = rb >> 2, cb = rb & 3;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 ka = z, va = z, kb = z, vb = z;
-    if (ja < n) {
-      const float* p = base + (size_t)ja * 3 * D + D + (h0 + hla) * HD + ca * 4;
-      ka = *reinterpret_cast<const float4*>(p);
-      va = *reinterpret_cast<const float4*>(p + D);
+  auto issue_load = [&](int h) {            // rows [0, n) of Q_h | K_h | V_h, 12 chunks of 16 bytes per row
+    for (int idx = lt; idx < n * 12; idx += lthreads) {
+      const int j = idx / 12, c = idx - j * 12;
+      cp_async16(raw + j * RAWS + c * 4, base + (size_t)j * 3 * D + (c >> 2) * D + h * HD + (c & 3) * 4);
     }
-    if (idx2 < items && jb < n) {
-      const float* p = base + (size_t)jb * 3 * D + D + (h0 + hlb) * HD + cb * 4;
-      kb = *reinterpret_cast<const float4*>(p);
-      vb = *reinterpret_cast<const float4*>(p + D);
-    }
-    float2* sKa = sm2 + hla * head_pairs;
-    stage_row(sKa + ja * KSTR + ca * 4, ka);
-    stage_row(sKa + npad * KSTR + ja * VSTR + ca * 4, va);
-    if (idx2 < items) {
-      float2* sKb = sm2 + hlb * head_pairs;
-      stage_row(sKb + jb * KSTR + cb * 4, kb);
-      stage_row(sKb + npad * KSTR + jb * VSTR + cb * 4, vb);
-    }
-  }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  for (int idx = lt; idx < (npad - n) * RAWS; idx += lthreads) raw[n * RAWS + idx] = 0.f;      // padding keys
+  issue_load(hl);
 
   // norm_factor = 1/sqrt(16) (graph_encoder.py:40,89) and log2(e) go into q once: the softmax runs in base 2
   const float qs = 0.25f * 1.4426950408889634f;
-  uint32_t qhi[2][4], qlo[2][4];
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) split_rn(qraw[ks][e] * qs, qhi[ks][e], qlo[ks][e]);
-  __syncthreads();
 
-  const uint2* kr = reinterpret_cast<const uint2*>(sm2 + hl * head_pairs) + g * KSTR + t;
-  const uint2* vr = reinterpret_cast<const uint2*>(sm2 + hl * head_pairs) + npad * KSTR + 2 * t * VSTR + g;
-  float om[2][4], ox[2][4];                 // O accumulators: main and cross products, dims [0,8) and [8,16)
+  for (int it = 0; it < nit; ++it) {
+    const int h = hl + it * hpc;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                        // raw rows of head h visible; previous head's fragments no longer read
+    uint32_t qhi[2][4], qlo[2][4];
 #pragma unroll
-  for (int d = 0; d < 2; ++d)
+    for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { om[d][e] = 0.f; ox[d][e] = 0.f; }
-  float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
-
-  for (int c = 0; c < nchunk; ++c, kr += CH * 8 * KSTR, vr += CH * 8 * VSTR) {
-    float s[CH][4];
-    // ---- S = Q K^T for 8 CH keys ----
-#pragma unroll
-    for (int jt = 0; jt < CH; ++jt) {
-      const uint2 k00 = kr[jt * 8 * KSTR], k01 = kr[jt * 8 * KSTR + 4], k10 = kr[jt * 8 * KSTR + 8], k11 = kr[jt * 8 * KSTR + 12];
-      s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
-      mma_tf32(s[jt], qlo[0], k00.x, k01.x);
-      mma_tf32(s[jt], qhi[0], k00.y, k01.y);
-      mma_tf32(s[jt], qlo[1], k10.x, k11.x);
-      mma_tf32(s[jt], qhi[1], k10.y, k11.y);
-      mma_tf32(s[jt], qhi[0], k00.x, k01.x);
-      mma_tf32(s[jt], qhi[1], k10.x, k11.x);
+      for (int e = 0; e < 4; ++e) {
+        const int r = (e & 1) ? r1 : r0;
+        const float q = (r < n) ? raw[r * RAWS + ks * 8 + t + ((e & 2) ? 4 : 0)] : 0.f;
+        split_rn(q * qs, qhi[ks][e], qlo[ks][e]);
+      }
     }
-    if ((c + 1) * CH * 8 > n) {               // the chunk holds padding keys: mask them
+    for (int idx = lt; idx < npad * 2; idx += lthreads) {          // K: (key j, dims 8 k2 .. 8 k2 + 7)
+      const int j = idx >> 1, k2 = idx & 1;
+      const float4* src = reinterpret_cast<const float4*>(raw + j * RAWS + HD + k2 * 8);
+      store_pairs(ksp + j * KSTR + k2 * 4, 8, src[0], src[1]);
+    }
+    for (int idx = lt; idx < npad * 2; idx += lthreads) {          // V: (keys 2 kp, 2 kp + 1; dims 4 c .. 4 c + 3)
+      const int kp = idx >> 2, c = idx & 3;
+      const float4 a = *reinterpret_cast<const float4*>(raw + (2 * kp) * RAWS + 2 * HD + c * 4);
+      const float4 bb = *reinterpret_cast<const float4*>(raw + (2 * kp + 1) * RAWS + 2 * HD + c * 4);
+      store_pairs(vsp + kp * VSTR + c * 4, 16, a, bb);
+    }
+    __syncthreads();                        // fragments visible; raw buffer free for the next head
+    if (it + 1 < nit) issue_load(h + hpc);
+
+    const uint2* kr = ksp + g * KSTR + t;
+    const uint2* vr = vsp + t * VSTR + g;
+    float om[2][4], ox[2][4];               // O accumulators: main and cross products, dims [0,8) and [8,16)
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { om[d][e] = 0.f; ox[d][e] = 0.f; }
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+
+    for (int c = 0; c < nchunk; ++c, kr += CH * 8 * KSTR, vr += CH * 4 * VSTR) {
+      float s[CH][4];
+      // ---- S = Q K^T for 8 CH keys ----
 #pragma unroll
       for (int jt = 0; jt < CH; ++jt) {
-        const int key = (c * CH + jt) * 8 + 2 * t;
-        if (key >= n) { s[jt][0] = -CUDART_INF_F; s[jt][2] = -CUDART_INF_F; }
-        if (key + 1 >= n) { s[jt][1] = -CUDART_INF_F; s[jt][3] = -CUDART_INF_F; }
+        const uint2* kt = kr + jt * 8 * KSTR;
+        const uint2 kh0 = kt[0], kh1 = kt[4], kl0 = kt[8], kl1 = kt[12];
+        s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
+        mma_tf32(s[jt], qlo[0], kh0);
+        mma_tf32(s[jt], qhi[0], kl0);
+        mma_tf32(s[jt], qlo[1], kh1);
+        mma_tf32(s[jt], qhi[1], kl1);
+        mma_tf32(s[jt], qhi[0], kh0);
+        mma_tf32(s[jt], qhi[1], kh1);
+      }
+      if ((c + 1) * CH * 8 > n) {             // the chunk holds padding keys: mask them
+#pragma unroll
+        for (int jt = 0; jt < CH; ++jt) {
+          const int key = (c * CH + jt) * 8 + 2 * t;
+          if (key >= n) { s[jt][0] = -CUDART_INF_F; s[jt][2] = -CUDART_INF_F; }
+          if (key + 1 >= n) { s[jt][1] = -CUDART_INF_F; s[jt][3] = -CUDART_INF_F; }
+        }
+      }
+      // ---- online softmax: raise the running maxima of rows r0 / r1 ----
+      float x0 = -CUDART_INF_F, x1 = -CUDART_INF_F;
+#pragma unroll
+      for (int jt = 0; jt < CH; ++jt) {
+        x0 = fmaxf(x0, fmaxf(s[jt][0], s[jt][1]));
+        x1 = fmaxf(x1, fmaxf(s[jt][2], s[jt][3]));
+      }
+      x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+      x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+      const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);        // finite: every chunk holds a valid key
+      if (c > 0) {
+        const float f0 = ex2(m0 - n0), f1 = ex2(m1 - n1);
+        l0 *= f0; l1 *= f1;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          om[d][0] *= f0; om[d][1] *= f0; ox[d][0] *= f0; ox[d][1] *= f0;
+          om[d][2] *= f1; om[d][3] *= f1; ox[d][2] *= f1; ox[d][3] *= f1;
+        }
+      }
+      m0 = n0; m1 = n1;
+      // ---- O += P V ----
+#pragma unroll
+      for (int jt = 0; jt < CH; ++jt) {
+        const float p0 = ex2(s[jt][0] - m0), p1 = ex2(s[jt][1] - m0), p2 = ex2(s[jt][2] - m1), p3 = ex2(s[jt][3] - m1);
+        l0 += p0 + p1; l1 += p2 + p3;
+        // A fragment: column t <- key 2t, column t+4 <- key 2t+1 (the V pairs follow the same order)
+        uint32_t ph[4], pl[4];
+        ph[0] = __float_as_uint(p0) & 0xffffe000u; ph[1] = __float_as_uint(p2) & 0xffffe000u;
+        ph[2] = __float_as_uint(p1) & 0xffffe000u; ph[3] = __float_as_uint(p3) & 0xffffe000u;
+        pl[0] = __float_as_uint(p0 - __uint_as_float(ph[0])) & 0xffffe000u;
+        pl[1] = __float_as_uint(p2 - __uint_as_float(ph[1])) & 0xffffe000u;
+        pl[2] = __float_as_uint(p1 - __uint_as_float(ph[2])) & 0xffffe000u;
+        pl[3] = __float_as_uint(p3 - __uint_as_float(ph[3])) & 0xffffe000u;
+        const uint2* vt = vr + jt * 4 * VSTR;
+        const uint2 vh0 = vt[0], vh1 = vt[8], vl0 = vt[16], vl1 = vt[24];
+        mma_tf32(om[0], ph, vh0);
+        mma_tf32(om[1], ph, vh1);
+        mma_tf32(ox[0], pl, vh0);
+        mma_tf32(ox[1], pl, vh1);
+        mma_tf32(ox[0], ph, vl0);
+        mma_tf32(ox[1], ph, vl1);
       }
     }
-    // ---- online softmax: raise the running maxima of rows r0 / r1 ----
-    float x0 = -CUDART_INF_F, x1 = -CUDART_INF_F;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
 #pragma unroll
-    for (int jt = 0; jt < CH; ++jt) {
-      x0 = fmaxf(x0, fmaxf(s[jt][0], s[jt][1]));
-      x1 = fmaxf(x1, fmaxf(s[jt][2], s[jt][3]));
+    for (int d = 0; d < 2; ++d) {
+      if (r0 < n)
+        *reinterpret_cast<float2*>(heads + ((size_t)b * n + r0) * D + h * HD + d * 8 + 2 * t) =
+            make_float2((om[d][0] + ox[d][0]) * i0, (om[d][1] + ox[d][1]) * i0);
+      if (r1 < n)
+        *reinterpret_cast<float2*>(heads + ((size_t)b * n + r1) * D + h * HD + d * 8 + 2 * t) =
+            make_float2((om[d][2] + ox[d][2]) * i1, (om[d][3] + ox[d][3]) * i1);
     }
-    x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
-    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
-    const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);          // finite: every chunk holds a valid key
-    if (c > 0) {
-      const float f0 = ex2(m0 - n0), f1 = ex2(m1 - n1);
-      l0 *= f0; l1 *= f1;
-#pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        om[d][0] *= f0; om[d][1] *= f0; ox[d][0] *= f0; ox[d][1] *= f0;
-        om[d][2] *= f1; om[d][3] *= f1; ox[d][2] *= f1; ox[d][3] *= f1;
-      }
-    }
-    m0 = n0; m1 = n1;
-    // ---- O += P V ----
-#pragma unroll
-    for (int jt = 0; jt < CH; ++jt) {
-      const float p0 = ex2(s[jt][0] - m0), p1 = ex2(s[jt][1] - m0), p2 = ex2(s[jt][2] - m1), p3 = ex2(s[jt][3] - m1);
-      l0 += p0 + p1; l1 += p2 + p3;
-      // A fragment: column t <- key 2t, column t+4 <- key 2t+1 (the V rows below follow the same order)
-      uint32_t ph[4], pl[4];
-      ph[0] = __float_as_uint(p0) & 0xffffe000u; ph[1] = __float_as_uint(p2) & 0xffffe000u;
-      ph[2] = __float_as_uint(p1) & 0xffffe000u; ph[3] = __float_as_uint(p3) & 0xffffe000u;
-      pl[0] = __float_as_uint(p0 - __uint_as_float(ph[0])) & 0xffffe000u;
-      pl[1] = __float_as_uint(p2 - __uint_as_float(ph[1])) & 0xffffe000u;
-      pl[2] = __float_as_uint(p1 - __uint_as_float(ph[2])) & 0xffffe000u;
-      pl[3] = __float_as_uint(p3 - __uint_as_float(ph[3])) & 0xffffe000u;
-      const uint2 v00 = vr[jt * 8 * VSTR], v01 = vr[jt * 8 * VSTR + VSTR], v10 = vr[jt * 8 * VSTR + 8], v11 = vr[jt * 8 * VSTR + VSTR + 8];
-      mma_tf32(om[0], ph, v00.x, v01.x);
-      mma_tf32(om[1], ph, v10.x, v11.x);
-      mma_tf32(ox[0], pl, v00.x, v01.x);
-      mma_tf32(ox[1], pl, v10.x, v11.x);
-      mma_tf32(ox[0], ph, v00.y, v01.y);
-      mma_tf32(ox[1], ph, v10.y, v11.y);
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-#pragma unroll
-  for (int d = 0; d < 2; ++d) {
-    if (r0 < n)
-      *reinterpret_cast<float2*>(heads + ((size_t)b * n + r0) * D + h * HD + d * 8 + 2 * t) =
-          make_float2((om[d][0] + ox[d][0]) * i0, (om[d][1] + ox[d][1]) * i0);
-    if (r1 < n)
-      *reinterpret_cast<float2*>(heads + ((size_t)b * n + r1) * D + h * HD + d * 8 + 2 * t) =
-          make_float2((om[d][2] + ox[d][2]) * i1, (om[d][3] + ox[d][3]) * i1);
   }
 }
 
 template <int CH, int MAXT, int MINB>
 int launch_ch2(const float* qkv, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
   const int npad = ceil_div(n, 8 * CH) * 8 * CH;
-  const size_t smem = (size_t)hpc * npad * (KSTR + VSTR) * sizeof(float2);
+  const size_t smem = (size_t)hpc * lane_bytes(npad);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     AGH_CUDA(cudaFuncSetAttribute(mha_mma_kernel<CH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  mha_mma_kernel<CH, MAXT, MINB><<<B * (H / hpc), hpc * mt * 32, smem, st>>>(qkv, n, hpc, mt, heads);
+  mha_mma_kernel<CH, MAXT, MINB><<<B, hpc * mt * 32, smem, st>>>(qkv, n, hpc, mt, heads);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
 }
@@ -228,9 +238,9 @@ int launch_ch2(const float* qkv, int B, int n, int hpc, int mt, float* heads, cu
 // CTAs of up to 8 warps (N <= 127) may use up to 128 registers; larger graphs need up to 19 warps per CTA.
 template <int CH>
 int launch_ch(const float* qkv, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
-  static const int minb = getenv("AGH_MHA_MINB") ? atoi(getenv("AGH_MHA_MINB")) : MHA_MINB_SMALL;
+  static const int minb = getenv("AGH_MHA_MINB") ? atoi(getenv("AGH_MHA_MINB")) : 2;
   if (hpc * mt <= 8 && minb == 3) return launch_ch2<CH, 256, 3>(qkv, B, n, hpc, mt, heads, st);
-  if (hpc * mt <= 8) return launch_ch2<CH, 256, MHA_MINB_SMALL>(qkv, B, n, hpc, mt, heads, st);
+  if (hpc * mt <= 8) return launch_ch2<CH, 256, 2>(qkv, B, n, hpc, mt, heads, st);
   return launch_ch2<CH, MHA_MAX_THREADS, 1>(qkv, B, n, hpc, mt, heads, st);
 }
 
@@ -241,13 +251,14 @@ int launch_mha_mma(const float* qkv, int B, int n, float* heads, cudaStream_t st
   int hpc = 1;
   while (hpc < H && 2 * hpc * mt <= 8) hpc *= 2;                 // about 8 warps per CTA for small graphs
   AGH_CHECK_ARG(hpc * mt * 32 <= MHA_MAX_THREADS);
-  // chunk length: least padded work (about 100 instructions per key fragment, 60 per chunk for the rescale)
+  // chunk length: least padded work (about 60 instructions per key fragment, 60 per chunk for the rescale)
   const int ntile = ceil_div(n, 8);
   int best = 8, best_cost = 1 << 30;
   for (int ch = 8; ch >= 3; --ch) {
-    const int chunks = ceil_div(ntile, ch), cost = chunks * ch * 100 + chunks * 60;
+    const int chunks = ceil_div(ntile, ch), cost = chunks * ch * 60 + chunks * 60;
     if (cost < best_cost) { best = ch; best_cost = cost; }
   }
+  if (getenv("AGH_MHA_CH")) best = atoi(getenv("AGH_MHA_CH"));
   switch (best) {
     case 3: return launch_ch<3>(qkv, B, n, hpc, mt, heads, st);
     case 4: return launch_ch<4>(qkv, B, n, hpc, mt, heads, st);
