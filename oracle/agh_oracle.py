@@ -406,6 +406,36 @@ def nearest_neighbor(task):
     return get_costs(task, pi), env.serve, pi
 
 
+def cws(task):
+    """Clarke-Wright savings heuristic, agh_baseline.py:17-77: second weight-free consumer of the environment
+    (known answer on the shipped agh20 set: 106354.4296875).  savings f64 = (d(0,j) + d(i,0) - d(i,j)) [f32]
+    - 0.03*60 * (tw_left[j] - tw_left[i] - duration[i] - d(i,j)/110 [f32]); at the depot the reference indexes the
+    savings with prev_a - 1 = -1, the row of the last flight."""
+    loc = task['loc']
+    B, N = loc.shape
+    table = task['distance'][0]
+    d_ij = table[NODE_SIZE * loc[:, :, None] + loc[:, None, :]]
+    savings_distance = table[loc][:, None, :] + table[NODE_SIZE * loc][:, :, None] - d_ij
+    tw_left, tw_right = task['tw_left'][:, 1:], task['tw_right'][:, 1:]
+    savings_time = tw_left[:, None, :] - tw_left[:, :, None]
+    savings_time = savings_time - task['duration'][:, :, None] - d_ij / 110.0
+    savings = savings_distance - 0.03 * 60 * savings_time
+    env = Env(task)
+    sel = 1 + tw_right.sort(dim=1)[1][:, 0]
+    env.update(sel)
+    seq = [sel]
+    rows = torch.arange(B)
+    while not env.all_finished():
+        score = savings[rows, env.prev[:, 0] - 1]
+        score = torch.cat((score.min(1, keepdim=True)[0] - 1, score), 1)
+        score[env.mask().bool()] = -math.inf
+        sel = score.sort(descending=True)[1][:, 0]
+        env.update(sel)
+        seq.append(sel)
+    pi = torch.stack(seq, 1)
+    return get_costs(task, pi), env.serve, pi
+
+
 def random_init_weights(seed: int = 1234) -> Dict[str, torch.Tensor]:
     """Same parameter creation order and initialisers as AttentionModel.__init__
     (attention_model.py:115-152, graph_encoder.py:42-54,124,165-168) so that torch.manual_seed(seed)

@@ -156,3 +156,21 @@ def test_run_cli_train_and_resume(tmp_path, capsys):
     from agh_b200.utils import load_model
     model, args = load_model(opts.save_dir)            # the run directory is a loadable model directory
     assert args['graph_size'] == 20 and model.is_agh
+
+
+@pytest.mark.parametrize('method,kat', [('nearest_neighbor', 147099.953125), ('cws', 106354.4296875)])
+def test_heuristic_baselines_reproduce_reference_kats(method, kat, capsys):
+    """agh_baseline.py val() with nearest_neighbor / cws over the device environment: per-fleet costs equal the
+    unmodified reference's on the shipped agh20 set (tests/golden/kat_agh20.npz) and the weight-free known answers
+    of SURVEY 4 / 8c are reproduced."""
+    from agh_b200 import AGH, agh_baseline
+    from agh_b200.nets.attention_model import load_fleet_info
+    g = load_golden('kat_agh20.npz')
+    fleet_info, distance = load_fleet_info()
+    opt = types.SimpleNamespace(val_method=method, graph_size=20, device=torch.device('cuda'), eval_batch_size=500,
+                                no_progress_bar=True)
+    total, per_fleet = agh_baseline.val(_dataset(20, 1000), opt, fleet_info, distance, AGH)
+    assert per_fleet.shape == (1000, 10)
+    assert np.allclose(per_fleet.numpy(), g[method + '_costs'], rtol=1e-6, atol=0)
+    assert abs(total.mean().item() - kat) / kat < 1e-6
+    assert 'Validation overall avg_cost' in capsys.readouterr().out

@@ -128,21 +128,25 @@ def test_reinforce_batch_agh20(weights, tables):
     assert np.allclose(W['project_step_context.weight'].grad.numpy(), g['grad_step_ctx'], rtol=1e-3, atol=1e-2)
 
 
-def test_env_kat_nearest_neighbor(tables):
-    """Weight-free KAT: the reference's nearest-neighbour heuristic (agh_baseline.py:80-101) on the shipped
-    agh20 set: avg cost 147099.953125."""
+@pytest.mark.parametrize('method,kat', [('nearest_neighbor', 147099.953125), ('cws', 106354.4296875)])
+def test_env_kat_heuristics(tables, method, kat):
+    """Weight-free KATs: the reference's nearest-neighbour (agh_baseline.py:80-101) and Clarke-Wright savings
+    (agh_baseline.py:17-77) heuristics on the shipped agh20 set: avg cost 147099.953125 / 106354.4296875, per-fleet
+    costs and serve times equal to the unmodified reference's."""
     g = load_golden('kat_agh20.npz')
     inst = make_instances(20)
     lv = O.new_tw_left_levels(inst)
-    costs = []
+    costs, serves = [], []
     for f in tables.order:
         task = O.fleet_task(tables, inst, f, lv)
-        c, serve, _ = O.nearest_neighbor(task)
+        c, serve, _ = getattr(O, method)(task)
         costs.append(c.numpy())
+        serves.append(serve[:16].numpy())
         O.chain_tw_left(tables, lv, f, serve)
     costs = np.stack(costs, 1)
-    assert np.array_equal(costs, g['nearest_neighbor_costs'])
-    assert torch.from_numpy(costs).sum(1).mean().item() == pytest.approx(147099.953125, abs=0)
+    assert np.array_equal(costs, g[method + '_costs'])
+    assert np.array_equal(np.stack(serves, 1), g[method + '_serve'])
+    assert torch.from_numpy(costs).sum(1).mean().item() == pytest.approx(kat, abs=0)
 
 
 def test_get_costs_rejects_bad_tours(weights, tables):
