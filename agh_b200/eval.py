@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import ops, parallel
-from .train import iter_batches, get_inner_model
+from .train import iter_batches, get_inner_model, fleet_rollout
 from .utils import load_model, move_to
 from .utils.functions import parse_softmax_temperature
 
@@ -41,7 +41,11 @@ def _eval_dataset(model, dataset, width, softmax_temp, opts, device):
                 assert width == 0, 'Do not set width when using greedy'
                 assert opts.eval_batch_size <= opts.max_calc_batch_size, \
                     'eval_batch_size should be smaller than calc batch size'
-                batch_rep, iter_rep = 1, 1
+                with torch.no_grad():                      # fleets of one precedence level share launches
+                    costs, _ = fleet_rollout(model, batch, device)
+                model.raise_pending()
+                cost.append(costs)
+                continue
             elif width * opts.eval_batch_size > opts.max_calc_batch_size:
                 assert opts.eval_batch_size == 1
                 assert width % opts.max_calc_batch_size == 0

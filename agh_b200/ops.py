@@ -76,6 +76,18 @@ def fleet_task(loc, type_, departure, demand_all, tw_left_levels, level: int, fl
     return FleetTask(coord, demand, tw_left, tw_right, duration, bool(nd_is_f32), fleet - 1)
 
 
+def cat_tasks(tasks) -> FleetTask:
+    """Concatenate the sub-problems of several fleets of ONE precedence level along the batch (per-instance fleet
+    ids; the tw_right dtype flag is a property of the level, so it is shared)."""
+    assert len({t.twr_f32 for t in tasks}) == 1
+    dev = tasks[0].coord.device
+    ids = torch.cat([t.fleet_ids if t.fleet_ids is not None else
+                     torch.full((t.B,), t.fleet, dtype=torch.int32, device=dev) for t in tasks])
+    return FleetTask(coord=torch.cat([t.coord for t in tasks]), demand=torch.cat([t.demand for t in tasks]),
+                     tw_left=torch.cat([t.tw_left for t in tasks]), tw_right=torch.cat([t.tw_right for t in tasks]),
+                     duration=torch.cat([t.duration for t in tasks]), twr_f32=tasks[0].twr_f32, fleet=-1, fleet_ids=ids)
+
+
 def chain_tw_left(tw_left_levels, level: int, serve) -> None:
     _, B, N = tw_left_levels.shape
     check(lib().agh_chain_tw_left(ptr(tw_left_levels, torch.float32), level, ptr(serve, torch.float32), B, N,

@@ -41,27 +41,49 @@ def iter_batches(dataset, batch_size, lo=0, hi=None, no_progress_bar=True):
             yield bat
 
 
-def fleet_rollout(model, bat, device, per_fleet=None):
+LEVEL_BATCH_LIMIT = 16384      # instance-fleets per launch up to which same-level fleets are solved together
+
+
+def fleet_rollout(model, bat, device, per_fleet=None, level_batch=None):
     """Solve the 10 fleets of one batch in order.  `bat`: dict of loc/arrival/departure/type/demand on any
-    device.  Returns (costs [B,10], lls list) on `device`; per_fleet(k, f, cost, ll, serve) is an optional hook."""
+    device.  Returns (costs [B,10], lls list) on `device`; per_fleet(k, f, cost, ll, serve) is an optional hook.
+
+    Fleets of one precedence level only read tw_left of their own level and max-accumulate into the next one
+    (train.py:42,67), so they are independent of each other.  In greedy eval mode (instances do not interact:
+    BatchNorm uses running statistics) they are concatenated along the batch and solved by ONE encode / decode
+    launch sequence -- 5 dependent stages instead of 10, which matters when B alone does not fill
+    the GPU.  Per-instance results are identical to the one-fleet-at-a-time order.  level_batch: None = automatic
+    (small batches, greedy eval), False = never."""
     inner = get_inner_model(model)
     info = inner.fleet_info
     x = move_to(bat, device)
     loc, type_ = x['loc'].contiguous(), x['type'].contiguous()
     departure, demand_all = x['departure'].contiguous(), x['demand'].contiguous()
+    B = loc.size(0)
     lv = x['arrival'].repeat(len(info['next_duration']) + 1, 1, 1).contiguous()         # [6,B,N]  (train.py:40)
-    costs, lls = [], []
-    for k, f in enumerate(info['order']):
+    order = list(info['order'])
+    if level_batch is None:
+        level_batch = (not inner.training) and getattr(inner, 'decode_type', None) == 'greedy'
+    groups = []                                    # consecutive fleets of `order` that share a precedence level
+    for k, f in enumerate(order):
         p = info['precedence'][f]
+        if level_batch and groups and groups[-1][0] == p and (len(groups[-1][1]) + 1) * B <= LEVEL_BATCH_LIMIT:
+            groups[-1][1].append((k, f))
+        else:
+            groups.append((p, [(k, f)]))
+    costs, lls = [None] * len(order), [None] * len(order)
+    for p, members in groups:
         nd = info['next_duration'][p]
-        task = ops.fleet_task(loc, type_, departure, demand_all, lv, p, f, info['duration'][f], nd,
-                              nd_is_f32=all(type(v) is float for v in nd))
+        tasks = [ops.fleet_task(loc, type_, departure, demand_all, lv, p, f, info['duration'][f], nd,
+                                nd_is_f32=all(type(v) is float for v in nd)) for _, f in members]
+        task = tasks[0] if len(tasks) == 1 else ops.cat_tasks(tasks)
         cost, ll, serve = model(task)
-        costs.append(cost)
-        lls.append(ll)
-        ops.chain_tw_left(lv, p, serve.contiguous())
-        if per_fleet is not None:
-            per_fleet(k, f, cost, ll, serve)
+        for i, (k, f) in enumerate(members):
+            c, l, s = cost[i * B:(i + 1) * B], ll[i * B:(i + 1) * B], serve[i * B:(i + 1) * B]
+            costs[k], lls[k] = c, l
+            ops.chain_tw_left(lv, p, s.contiguous())
+            if per_fleet is not None:
+                per_fleet(k, f, c, l, s)
     return torch.stack(costs, 1), lls
 
 

@@ -174,3 +174,23 @@ def test_heuristic_baselines_reproduce_reference_kats(method, kat, capsys):
     assert np.allclose(per_fleet.numpy(), g[method + '_costs'], rtol=1e-6, atol=0)
     assert abs(total.mean().item() - kat) / kat < 1e-6
     assert 'Validation overall avg_cost' in capsys.readouterr().out
+
+
+@pytest.mark.parametrize('n,B', [(20, 64), (50, 100)])
+def test_level_batched_fleets_equal_sequential(cuda_model, n, B):
+    """solving the fleets of one precedence level in one launch sequence (5 stages) gives exactly
+    the per-instance costs, log-likelihoods and chained time windows of the reference's 10-stage order."""
+    from agh_b200.train import fleet_rollout
+    cuda_model.set_decode_type('greedy')
+    bat = {k: v[:B] for k, v in make_instances(n).items()}
+    seen = {}
+    with torch.no_grad():
+        c_seq, ll_seq = fleet_rollout(cuda_model, bat, torch.device('cuda'), level_batch=False,
+                                      per_fleet=lambda k, f, c, l, s: seen.setdefault(('seq', f), s.clone()))
+        c_lvl, ll_lvl = fleet_rollout(cuda_model, bat, torch.device('cuda'), level_batch=True,
+                                      per_fleet=lambda k, f, c, l, s: seen.setdefault(('lvl', f), s.clone()))
+    assert torch.equal(c_seq, c_lvl)
+    for a, b in zip(ll_seq, ll_lvl):
+        assert torch.equal(a, b)
+    for f in range(1, 11):
+        assert torch.equal(seen[('seq', f)], seen[('lvl', f)])
