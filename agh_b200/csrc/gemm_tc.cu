@@ -149,7 +149,8 @@ struct Cfg {
   static constexpr int NACC = WRES ? 1 : 3;
   static constexpr int NBUF = WRES ? 2 : 1;
   static constexpr int NBARS = 3 * STAGES + 2 * NBUF + 2;
-  static constexpr int SMEM = WRES_BYTES + STAGES * STAGE_BYTES + 1024 /*align*/ + 8 * NBARS + 16;
+  static constexpr int VEC_OFF = (8 * NBARS + 16 + 15) & ~15;      // per-column epilogue vectors: bias, bn scale, bn shift
+  static constexpr int SMEM = WRES_BYTES + STAGES * STAGE_BYTES + 1024 /*align*/ + VEC_OFF + 3 * BN * 4;
 };
 
 // Which epilogues go through the in-register 32x32 transpose (coalesced 128-byte rows) instead of the row-wise
@@ -181,12 +182,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_wraw = bar_base + 8 * (3 * STAGES + 2 * C::NBUF);
   const uint32_t bar_wsplit = bar_wraw + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 * C::NBARS);
+  float* s_vec = reinterpret_cast<float*>(bars + C::VEC_OFF);   // [bias | bn_s | bn_t] of this CTA's 128 columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
   const int nkb = g.K / BK;
   const int num_mt = (g.M + BM - 1) / BM;
 
+  // The epilogue's per-column vectors are constant for the CTA: staged once, so that no global-memory latency sits
+  // between the accumulator read and the stores of every tile.
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {
+    const int t = threadIdx.x - 64, c = n0 + t;
+    s_vec[t] = g.bias != nullptr ? g.bias[c] : 0.f;
+    s_vec[BN + t] = g.bn_s != nullptr ? g.bn_s[c] : 1.f;
+    s_vec[2 * BN + t] = g.bn_t != nullptr ? g.bn_t[c] : 0.f;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_raw(s), 1);
@@ -348,16 +358,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int col = n0 + c0 + v4 * 4;
             float4 v = make_float4(r[4 * v4], r[4 * v4 + 1], r[4 * v4 + 2], r[4 * v4 + 3]);
             if (EPI == EPI_BIAS_RELU) {
-              const float4 bb = *reinterpret_cast<const float4*>(g.bias + col);
+              const float4 bb = *reinterpret_cast<const float4*>(s_vec + c0 + v4 * 4);
               v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f); v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
             } else if (EPI == EPI_RES_BN) {
               if (g.bias != nullptr) {
-                const float4 bb = *reinterpret_cast<const float4*>(g.bias + col);
+                const float4 bb = *reinterpret_cast<const float4*>(s_vec + c0 + v4 * 4);
                 v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
               }
               const float4 rr = __ldg(reinterpret_cast<const float4*>(g.res + (size_t)row * g.ldr + col));
-              const float4 sc = *reinterpret_cast<const float4*>(g.bn_s + col);
-              const float4 sh = *reinterpret_cast<const float4*>(g.bn_t + col);
+              const float4 sc = *reinterpret_cast<const float4*>(s_vec + BN + c0 + v4 * 4);
+              const float4 sh = *reinterpret_cast<const float4*>(s_vec + 2 * BN + c0 + v4 * 4);
               v.x = fmaf(rr.x + v.x, sc.x, sh.x); v.y = fmaf(rr.y + v.y, sc.y, sh.y);
               v.z = fmaf(rr.z + v.z, sc.z, sh.z); v.w = fmaf(rr.w + v.w, sc.w, sh.w);
             }
@@ -391,8 +401,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int col = n0 + c0 + lane;
         float bias = 0.f, sc = 1.f, sh = 0.f;
-        if (EPI == EPI_BIAS_RELU || (EPI == EPI_RES_BN && g.bias != nullptr)) bias = g.bias[col];
-        if (EPI == EPI_RES_BN) { sc = g.bn_s[col]; sh = g.bn_t[col]; }
+        if (EPI == EPI_BIAS_RELU || (EPI == EPI_RES_BN && g.bias != nullptr)) bias = s_vec[c0 + lane];
+        if (EPI == EPI_RES_BN) { sc = s_vec[BN + c0 + lane]; sh = s_vec[2 * BN + c0 + lane]; }
         int mat = 0, cc = 0, bi = 0, j = 0;
         if (EPI == EPI_DEC) { mat = col / D; cc = col % D; bi = row0 / g.n; j = row0 % g.n; }
         if (EPI == EPI_RES_BN) {
