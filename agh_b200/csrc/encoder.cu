@@ -1,15 +1,17 @@
-// Graph-attention encoder (eval-mode BatchNorm) and decoder precompute, fp32 CUDA-core path.
+// Graph-attention encoder (eval-mode BatchNorm) and decoder precompute: the layer driver, and the fp32 CUDA-core
+// kernels (SGEMM, attention) that the tensor-core path (gemm_tc.cu, mha_mma.cu) is validated against.
 //
 //   agh_init_embed : attention_model.py:272-294
 //   agh_encode     : graph_encoder.py:56-111 (MHA), :135-143 (BatchNorm1d, running stats),
 //                    :146-172 (layer = MHA+skip, BN, FF+skip, BN), :195-207
 //   agh_precompute : attention_model.py:392-414, :604-611
 //
-// All dense contractions go through one tiled SGEMM (128x128x16 tiles, 8x8 register micro-tile,
-// register double buffering) whose epilogue fuses bias / ReLU / residual + BatchNorm scale-shift /
-// the scatter into the padded key layout the decode kernel stages with TMA.  Self-attention is a
-// flash-style kernel: one CTA per (instance, head), K_h/V_h staged in shared memory, one query row
-// per thread with an online softmax, so no [n,n] score matrix ever reaches HBM.
+// CUDA-core back end (agh_set_gemm_backend(0) / AGH_GEMM=simt): all dense contractions go through one tiled SGEMM
+// (128x128x16 tiles, 8x8 register micro-tile, register double buffering) whose epilogue fuses bias / ReLU /
+// residual + BatchNorm scale-shift / the scatter into the swizzled key layout the decode kernel stages with TMA;
+// self-attention is a flash-style kernel: two heads per CTA, K_h/V_h staged in shared memory, two query rows per
+// thread with a base-2 online softmax, so no [n,n] score matrix ever reaches HBM.  The default back end replaces
+// both with tensor-core kernels behind the same launch sequence.
 #include "common.cuh"
 #include "gemm.cuh"
 #include <math_constants.h>
