@@ -37,7 +37,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + srcs
+    extra = os.environ.get('AGH_NVCC_EXTRA', '').split()          # e.g. -DAGH_TC_TRANSPOSE_MASK=0x7 for A/B builds
+    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise AghError('nvcc failed:\n' + res.stdout + res.stderr)

@@ -154,12 +154,13 @@ struct Cfg {
 };
 
 // Which epilogues go through the in-register 32x32 transpose (coalesced 128-byte rows) instead of the row-wise
-// 16-byte accesses: bit EPI of the mask.  Overridable at compile time for A/B measurements.  Measured per launch at
-// M = 1.01 M rows (transposed vs row-wise): QKV/plain 688 vs 1010 us, out-proj 615 vs 636, FF2 1070 vs 1260 (both
-// residual+BN, with the residual prefetched), FF1/bias+ReLU 2215 vs 1560, key scatter 2750 vs 1150 -> plain and
-// residual+BN epilogues are transposed, the two 512-column outputs stay row-wise.
+// 16-byte accesses: bit EPI of the mask.  Overridable at compile time for A/B measurements
+// (AGH_NVCC_EXTRA=-DAGH_TC_TRANSPOSE_MASK=..).  Measured per launch at M = 1.01 M rows with the eight epilogue
+// warps (transposed vs row-wise): QKV/plain 612 vs ~1000 us, out-proj 508 vs ~630, FF2 1010 vs ~1250 (residual+BN
+// with the residual prefetched), FF1/bias+ReLU 820 vs 1200, key scatter 1690 vs 1250 -> everything but the
+// swizzled key scatter is transposed.  (With four epilogue warps the shuffles made FF1 slower transposed.)
 #ifndef AGH_TC_TRANSPOSE_MASK
-#define AGH_TC_TRANSPOSE_MASK 0x5
+#define AGH_TC_TRANSPOSE_MASK 0x7
 #endif
 __host__ __device__ constexpr bool epi_transposed(int epi) { return (AGH_TC_TRANSPOSE_MASK >> epi) & 1; }
 
