@@ -9,14 +9,20 @@
 // are issued first so the small terms enter the accumulator before the large ones; for O (a sum over all keys) they
 // have their own accumulator so that they are not absorbed by the growing partial sums.
 //
-// One CTA walks the heads of one instance.  The raw Q_h|K_h|V_h rows of the NEXT head stream into shared memory
-// with cp.async while the warps work on the current one, so the global-memory latency is paid once per instance.
-// A short pass then rewrites K_h and V_h as TF32 (hi, lo) values in fragment order: the two B-fragment registers
-// of every mma are adjacent in shared memory (K: columns t and t+4 of one key; V: keys 2t and 2t+1 of one column),
-// so each fragment is ONE LDS.64 straight into the register pair the instruction needs.  Row strides (20 and 36
-// pairs) keep those loads bank-conflict free.  The P fragments of the second product are the score fragments
-// themselves: a thread's score columns (2t, 2t+1) are fed as A-columns (t, t+4) and the V pairs follow the same
-// key order, so no shuffle is needed between the two products.
+// One CTA walks the 8 heads of one instance.  K_h and V_h are rewritten in shared memory as TF32 (hi, lo) values in
+// fragment order: the two B-fragment registers of every mma are adjacent (K: columns t and t+4 of one key; V: keys
+// 2t and 2t+1 of one column), so each fragment is ONE LDS.64 straight into the register pair the instruction needs;
+// row strides of 20 and 36 pairs keep those loads bank-conflict free.  The P fragments of the second product are the
+// score fragments themselves: a thread's score columns (2t, 2t+1) are fed as A-columns (t, t+4) and the V pairs
+// follow the same key order, so no shuffle is needed between the two products.
+//
+// Two kernels share that inner routine:
+//  * mha_ws_kernel (default when it fits): warp-specialised.  One producer warp streams the raw Q_h|K_h|V_h rows of
+//    the next head with cp.async.bulk (mbarrier complete_tx) and converts K_h, V_h into the fragment-ordered buffer
+//    of a two-deep ring; the compute warps only wait on the ring's full/empty mbarriers, so the HMMA pipe is never
+//    idled by a staging phase or a CTA-wide barrier.
+//  * mha_mma_kernel: every warp stages and computes (cp.async prefetch of the next head, two __syncthreads per
+//    head); used for small graphs (several heads per CTA) and when the ring does not fit in shared memory.
 #include "common.cuh"
 #include "gemm.cuh"
 #include <math_constants.h>
@@ -26,10 +32,14 @@ namespace agh {
 
 namespace {
 
-constexpr int RAWS = 52;          // raw row stride in floats: Q 16 | K 16 | V 16 | pad 4
+constexpr int RAWS = 52;          // mha_mma_kernel raw row stride in floats: Q 16 | K 16 | V 16 | pad 4
+constexpr int KVS = 36;           // mha_ws_kernel raw K|V row stride in floats: K 16 | V 16 | pad 4
+constexpr int QS = 20;            // mha_ws_kernel raw Q row stride in floats: Q 16 | pad 4
 constexpr int KSTR = 20;          // split K row (one key): 8 hi pairs, 8 lo pairs, 4 pad
 constexpr int VSTR = 36;          // split V row (two keys): 16 hi pairs, 16 lo pairs, 4 pad
 constexpr int MHA_MAX_THREADS = 640;
+// norm_factor = 1/sqrt(16) (graph_encoder.py:40,89) and log2(e) go into q once: the softmax runs in base 2
+constexpr float QSCALE = 0.25f * 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t tf32_rn(float x) {          // round to nearest TF32 (ties away), finite inputs
   return (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
@@ -38,6 +48,19 @@ __device__ __forceinline__ void split_rn(float x, uint32_t& hi, uint32_t& lo) {
   hi = tf32_rn(x);
   lo = tf32_rn(x - __uint_as_float(hi));
 }
+// hi = x truncated to TF32, lo = (x - hi) truncated: 3 operations instead of 5; |x - hi - lo| <= 2^-21 |x|
+__device__ __forceinline__ void split_tr(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+#ifndef AGH_MHA_SPLIT_TRUNC
+#define AGH_MHA_SPLIT_TRUNC 0
+#endif
+#if AGH_MHA_SPLIT_TRUNC
+#define SPLIT_KV split_tr
+#else
+#define SPLIT_KV split_rn
+#endif
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -48,14 +71,42 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
 }
 // (a_i, b_i), i = 0..3  ->  4 hi pairs at dst[0..3], 4 lo pairs at dst[lo_off..lo_off+3]
 __device__ __forceinline__ void store_pairs(uint2* dst, int lo_off, const float4 a, const float4 b) {
   uint32_t ah[4], al[4], bh[4], bl[4];
-  split_rn(a.x, ah[0], al[0]); split_rn(a.y, ah[1], al[1]); split_rn(a.z, ah[2], al[2]); split_rn(a.w, ah[3], al[3]);
-  split_rn(b.x, bh[0], bl[0]); split_rn(b.y, bh[1], bl[1]); split_rn(b.z, bh[2], bl[2]); split_rn(b.w, bh[3], bl[3]);
+  SPLIT_KV(a.x, ah[0], al[0]); SPLIT_KV(a.y, ah[1], al[1]); SPLIT_KV(a.z, ah[2], al[2]); SPLIT_KV(a.w, ah[3], al[3]);
+  SPLIT_KV(b.x, bh[0], bl[0]); SPLIT_KV(b.y, bh[1], bl[1]); SPLIT_KV(b.z, bh[2], bl[2]); SPLIT_KV(b.w, bh[3], bl[3]);
   uint4* d = reinterpret_cast<uint4*>(dst);
   d[0] = make_uint4(ah[0], bh[0], ah[1], bh[1]);
   d[1] = make_uint4(ah[2], bh[2], ah[3], bh[3]);
@@ -63,15 +114,216 @@ __device__ __forceinline__ void store_pairs(uint2* dst, int lo_off, const float4
   e[0] = make_uint4(al[0], bl[0], al[1], bl[1]);
   e[1] = make_uint4(al[2], bl[2], al[3], bl[3]);
 }
+// K_h / V_h rows [0, npad) (zeros beyond n) -> fragment-ordered (hi, lo) pairs; `raw` rows hold K at koff, V at voff
+__device__ __forceinline__ void split_kv(const float* raw, int rstride, int koff, int voff, int n, int npad, uint2* ksp,
+                                         uint2* vsp, int tid, int nthreads) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int idx = tid; idx < npad * 2; idx += nthreads) {            // K: (key j, dims 8 k2 .. 8 k2 + 7)
+    const int j = idx >> 1, k2 = idx & 1;
+    const float4* src = reinterpret_cast<const float4*>(raw + j * rstride + koff + k2 * 8);
+    const bool ok = j < n;
+    store_pairs(ksp + j * KSTR + k2 * 4, 8, ok ? src[0] : z, ok ? src[1] : z);
+  }
+  for (int idx = tid; idx < npad * 2; idx += nthreads) {            // V: (keys 2 kp, 2 kp + 1; dims 4 c .. 4 c + 3)
+    const int kp = idx >> 2, c = idx & 3;
+    const float4 a = (2 * kp < n) ? *reinterpret_cast<const float4*>(raw + (2 * kp) * rstride + voff + c * 4) : z;
+    const float4 b = (2 * kp + 1 < n) ? *reinterpret_cast<const float4*>(raw + (2 * kp + 1) * rstride + voff + c * 4) : z;
+    store_pairs(vsp + kp * VSTR + c * 4, 16, a, b);
+  }
+}
 
+// One warp, 16 query rows (fragments qhi/qlo), all keys of one head: out[d][e] = normalised O in the mma C layout
+// (e = 0,1: row r0, dims 8d + 2t, +1;  e = 2,3: row r0 + 8).  kr / vr point at this lane's first K / V fragment.
+template <int CH>
+__device__ __forceinline__ void attend(const uint2* kr, const uint2* vr, const uint32_t (&qhi)[2][4],
+                                       const uint32_t (&qlo)[2][4], int n, int nchunk, int t, float (&out)[2][4]) {
+  // O accumulators, dims [0,8) and [8,16): main product and the two cross products (three independent mma chains)
+  float om[2][4], ox[2][4], oy[2][4];
+#pragma unroll
+  for (int d = 0; d < 2; ++d)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { om[d][e] = 0.f; ox[d][e] = 0.f; oy[d][e] = 0.f; }
+  float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+
+  for (int c = 0; c < nchunk; ++c, kr += CH * 8 * KSTR, vr += CH * 4 * VSTR) {
+    float s[CH][4];
+    // ---- S = Q K^T for 8 CH keys ----
+#pragma unroll
+    for (int jt = 0; jt < CH; ++jt) {
+      const uint2* kt = kr + jt * 8 * KSTR;
+      const uint2 kh0 = kt[0], kh1 = kt[4], kl0 = kt[8], kl1 = kt[12];
+      s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
+      mma_tf32(s[jt], qlo[0], kh0);
+      mma_tf32(s[jt], qhi[0], kl0);
+      mma_tf32(s[jt], qlo[1], kh1);
+      mma_tf32(s[jt], qhi[1], kl1);
+      mma_tf32(s[jt], qhi[0], kh0);
+      mma_tf32(s[jt], qhi[1], kh1);
+    }
+    if ((c + 1) * CH * 8 > n) {             // the chunk holds padding keys: mask them
+#pragma unroll
+      for (int jt = 0; jt < CH; ++jt) {
+        const int key = (c * CH + jt) * 8 + 2 * t;
+        if (key >= n) { s[jt][0] = -CUDART_INF_F; s[jt][2] = -CUDART_INF_F; }
+        if (key + 1 >= n) { s[jt][1] = -CUDART_INF_F; s[jt][3] = -CUDART_INF_F; }
+      }
+    }
+    // ---- online softmax: raise the running maxima of rows r0 / r0 + 8 ----
+    float x0 = -CUDART_INF_F, x1 = -CUDART_INF_F;
+#pragma unroll
+    for (int jt = 0; jt < CH; ++jt) {
+      x0 = fmaxf(x0, fmaxf(s[jt][0], s[jt][1]));
+      x1 = fmaxf(x1, fmaxf(s[jt][2], s[jt][3]));
+    }
+    x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+    const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);        // finite: every chunk holds a valid key
+    if (c > 0) {
+      const float f0 = ex2(m0 - n0), f1 = ex2(m1 - n1);
+      l0 *= f0; l1 *= f1;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        om[d][0] *= f0; om[d][1] *= f0; ox[d][0] *= f0; ox[d][1] *= f0; oy[d][0] *= f0; oy[d][1] *= f0;
+        om[d][2] *= f1; om[d][3] *= f1; ox[d][2] *= f1; ox[d][3] *= f1; oy[d][2] *= f1; oy[d][3] *= f1;
+      }
+    }
+    m0 = n0; m1 = n1;
+    // ---- O += P V ----
+#pragma unroll
+    for (int jt = 0; jt < CH; ++jt) {
+      const float p0 = ex2(s[jt][0] - m0), p1 = ex2(s[jt][1] - m0), p2 = ex2(s[jt][2] - m1), p3 = ex2(s[jt][3] - m1);
+      l0 += p0 + p1; l1 += p2 + p3;
+      // A fragment: column t <- key 2t, column t+4 <- key 2t+1 (the V pairs follow the same order)
+      uint32_t ph[4], pl[4];
+      ph[0] = __float_as_uint(p0) & 0xffffe000u; ph[1] = __float_as_uint(p2) & 0xffffe000u;
+      ph[2] = __float_as_uint(p1) & 0xffffe000u; ph[3] = __float_as_uint(p3) & 0xffffe000u;
+      pl[0] = __float_as_uint(p0 - __uint_as_float(ph[0])) & 0xffffe000u;
+      pl[1] = __float_as_uint(p2 - __uint_as_float(ph[1])) & 0xffffe000u;
+      pl[2] = __float_as_uint(p1 - __uint_as_float(ph[2])) & 0xffffe000u;
+      pl[3] = __float_as_uint(p3 - __uint_as_float(ph[3])) & 0xffffe000u;
+      const uint2* vt = vr + jt * 4 * VSTR;
+      const uint2 vh0 = vt[0], vh1 = vt[8], vl0 = vt[16], vl1 = vt[24];
+      mma_tf32(om[0], ph, vh0);
+      mma_tf32(om[1], ph, vh1);
+      mma_tf32(ox[0], pl, vh0);
+      mma_tf32(ox[1], pl, vh1);
+      mma_tf32(oy[0], ph, vl0);
+      mma_tf32(oy[1], ph, vl1);
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    out[d][0] = (om[d][0] + (ox[d][0] + oy[d][0])) * i0; out[d][1] = (om[d][1] + (ox[d][1] + oy[d][1])) * i0;
+    out[d][2] = (om[d][2] + (ox[d][2] + oy[d][2])) * i1; out[d][3] = (om[d][3] + (ox[d][3] + oy[d][3])) * i1;
+  }
+}
+
+__device__ __forceinline__ void store_rows(float* heads_bh, int n, int r0, int t, const float (&out)[2][4]) {
+  // heads_bh = heads + b * n * D + h * HD
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    if (r0 < n) *reinterpret_cast<float2*>(heads_bh + (size_t)r0 * D + d * 8 + 2 * t) = make_float2(out[d][0], out[d][1]);
+    if (r0 + 8 < n) *reinterpret_cast<float2*>(heads_bh + (size_t)(r0 + 8) * D + d * 8 + 2 * t) = make_float2(out[d][2], out[d][3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// warp-specialised kernel: grid = B CTAs, block = (mt + 1) warps; warps 0..mt-1 compute, warp mt produces
+// ------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t ws_smem_bytes(int n, int npad) {
+  return 2 * (size_t)n * KVS * 4 + 2 * ((size_t)npad * KSTR * 8 + (size_t)(npad / 2) * VSTR * 8) + 64;
+}
+
+template <int CH, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) mha_ws_kernel(const float* __restrict__ qkv, int n, int mt,
+                                                            float* __restrict__ heads) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nchunk = (n + 8 * CH - 1) / (8 * CH), npad = nchunk * 8 * CH;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = qkv + (size_t)b * n * (3 * D);
+  float* raw_kv = reinterpret_cast<float*>(smem_raw);                       // [2][n][KVS]  raw K_h | V_h rows
+  uint2* ring = reinterpret_cast<uint2*>(raw_kv + 2 * n * KVS);             // [2]{ K [npad][KSTR], V [npad/2][VSTR] }
+  const int ring_pairs = npad * KSTR + (npad / 2) * VSTR;
+  uint64_t* split_full = reinterpret_cast<uint64_t*>(ring + 2 * ring_pairs);
+  uint64_t* split_empty = split_full + 2;
+
+  if (threadIdx.x == 0) {
+    mbar_init(split_full, 1); mbar_init(split_full + 1, 1);
+    mbar_init(split_empty, mt); mbar_init(split_empty + 1, mt);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == mt) {
+    // ================= producer warp =================
+    auto issue_load = [&](int h) {           // K_h | V_h rows -> raw_kv[h & 1], 8 chunks of 16 bytes per row
+      float* dst = raw_kv + (h & 1) * n * KVS;
+      for (int idx = lane; idx < n * 8; idx += 32) {
+        const int j = idx >> 3, c = idx & 7;
+        cp_async16(dst + j * KVS + c * 4, base + (size_t)j * 3 * D + (1 + (c >> 2)) * D + h * HD + (c & 3) * 4);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue_load(0);
+    for (int h = 0; h < H; ++h) {
+      const int bf = h & 1, use = h >> 1;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");           // rows of head h have landed
+      __syncwarp();                                                  // ... for every lane; head h-1's raw rows are dead
+      if (h + 1 < H) issue_load(h + 1);                              // flies during the conversion below
+      if (use >= 1) mbar_wait(split_empty + bf, (use - 1) & 1);      // compute warps are done with this ring slot
+      uint2* ksp = ring + bf * ring_pairs;
+      split_kv(raw_kv + bf * n * KVS, KVS, 0, HD, n, npad, ksp, ksp + npad * KSTR, lane, 32);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(split_full + bf);                   // release: fragments visible to the consumers
+    }
+  } else {
+    // ================= compute warps =================
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 16 + g, r1 = r0 + 8;
+    auto load_q = [&](int h, float (&q)[2][4]) {                     // this lane's A-fragment elements of Q_h
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = (e & 1) ? r1 : r0;
+          q[ks][e] = (r < n) ? __ldg(base + (size_t)r * 3 * D + h * HD + ks * 8 + t + ((e & 2) ? 4 : 0)) : 0.f;
+        }
+      }
+    };
+    float qraw[2][4];
+    load_q(0, qraw);
+    for (int h = 0; h < H; ++h) {
+      const int bf = h & 1;
+      uint32_t qhi[2][4], qlo[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_rn(qraw[ks][e] * QSCALE, qhi[ks][e], qlo[ks][e]);
+      if (h + 1 < H) load_q(h + 1, qraw);                            // in flight during this head
+      mbar_wait(split_full + bf, (h >> 1) & 1);
+      const uint2* ksp = ring + bf * ring_pairs;
+      float out[2][4];
+      attend<CH>(ksp + g * KSTR + t, ksp + npad * KSTR + t * VSTR + g, qhi, qlo, n, nchunk, t, out);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(split_empty + bf);                  // the ring slot may be refilled
+      store_rows(heads + (size_t)b * n * D + h * HD, n, r0, t, out);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// uniform kernel: grid = B CTAs, block = hpc * mt warps.  The CTA's warps form hpc "head lanes" of mt warps; lane hl
+// walks heads hl, hl + hpc, ... of the instance, warp (w % mt) of a lane owning query rows [16 (w % mt), +16).  The raw
+// rows of the next head arrive by cp.async while the current head is computed.
+// ------------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t lane_bytes(int npad) {
   return (size_t)npad * RAWS * 4 + (size_t)npad * KSTR * 8 + (size_t)(npad / 2) * VSTR * 8;
 }
 
-// grid = B CTAs, block = hpc * mt warps.  The CTA's warps form hpc "head lanes" of mt warps; lane hl walks heads
-// hl, hl + hpc, ... of the instance, warp (w % mt) of a lane owning query rows [16 (w % mt), +16).  CH = key
-// fragments (8 keys each) per online-softmax chunk; shared-memory rows are zero-padded to whole chunks, so the
-// chunk body is branch-free.
 template <int CH, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __restrict__ qkv, int n, int hpc, int mt,
                                                              float* __restrict__ heads) {
@@ -96,12 +348,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __rest
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-
-  for (int idx = lt; idx < (npad - n) * RAWS; idx += lthreads) raw[n * RAWS + idx] = 0.f;      // padding keys
   issue_load(hl);
-
-  // norm_factor = 1/sqrt(16) (graph_encoder.py:40,89) and log2(e) go into q once: the softmax runs in base 2
-  const float qs = 0.25f * 1.4426950408889634f;
 
   for (int it = 0; it < nit; ++it) {
     const int h = hl + it * hpc;
@@ -114,115 +361,20 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __rest
       for (int e = 0; e < 4; ++e) {
         const int r = (e & 1) ? r1 : r0;
         const float q = (r < n) ? raw[r * RAWS + ks * 8 + t + ((e & 2) ? 4 : 0)] : 0.f;
-        split_rn(q * qs, qhi[ks][e], qlo[ks][e]);
+        split_rn(q * QSCALE, qhi[ks][e], qlo[ks][e]);
       }
     }
-    for (int idx = lt; idx < npad * 2; idx += lthreads) {          // K: (key j, dims 8 k2 .. 8 k2 + 7)
-      const int j = idx >> 1, k2 = idx & 1;
-      const float4* src = reinterpret_cast<const float4*>(raw + j * RAWS + HD + k2 * 8);
-      store_pairs(ksp + j * KSTR + k2 * 4, 8, src[0], src[1]);
-    }
-    for (int idx = lt; idx < npad * 2; idx += lthreads) {          // V: (keys 2 kp, 2 kp + 1; dims 4 c .. 4 c + 3)
-      const int kp = idx >> 2, c = idx & 3;
-      const float4 a = *reinterpret_cast<const float4*>(raw + (2 * kp) * RAWS + 2 * HD + c * 4);
-      const float4 bb = *reinterpret_cast<const float4*>(raw + (2 * kp + 1) * RAWS + 2 * HD + c * 4);
-      store_pairs(vsp + kp * VSTR + c * 4, 16, a, bb);
-    }
+    split_kv(raw, RAWS, HD, 2 * HD, n, npad, ksp, vsp, lt, lthreads);
     __syncthreads();                        // fragments visible; raw buffer free for the next head
     if (it + 1 < nit) issue_load(h + hpc);
-
-    const uint2* kr = ksp + g * KSTR + t;
-    const uint2* vr = vsp + t * VSTR + g;
-    float om[2][4], ox[2][4];               // O accumulators: main and cross products, dims [0,8) and [8,16)
-#pragma unroll
-    for (int d = 0; d < 2; ++d)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { om[d][e] = 0.f; ox[d][e] = 0.f; }
-    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
-
-    for (int c = 0; c < nchunk; ++c, kr += CH * 8 * KSTR, vr += CH * 4 * VSTR) {
-      float s[CH][4];
-      // ---- S = Q K^T for 8 CH keys ----
-#pragma unroll
-      for (int jt = 0; jt < CH; ++jt) {
-        const uint2* kt = kr + jt * 8 * KSTR;
-        const uint2 kh0 = kt[0], kh1 = kt[4], kl0 = kt[8], kl1 = kt[12];
-        s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
-        mma_tf32(s[jt], qlo[0], kh0);
-        mma_tf32(s[jt], qhi[0], kl0);
-        mma_tf32(s[jt], qlo[1], kh1);
-        mma_tf32(s[jt], qhi[1], kl1);
-        mma_tf32(s[jt], qhi[0], kh0);
-        mma_tf32(s[jt], qhi[1], kh1);
-      }
-      if ((c + 1) * CH * 8 > n) {             // the chunk holds padding keys: mask them
-#pragma unroll
-        for (int jt = 0; jt < CH; ++jt) {
-          const int key = (c * CH + jt) * 8 + 2 * t;
-          if (key >= n) { s[jt][0] = -CUDART_INF_F; s[jt][2] = -CUDART_INF_F; }
-          if (key + 1 >= n) { s[jt][1] = -CUDART_INF_F; s[jt][3] = -CUDART_INF_F; }
-        }
-      }
-      // ---- online softmax: raise the running maxima of rows r0 / r1 ----
-      float x0 = -CUDART_INF_F, x1 = -CUDART_INF_F;
-#pragma unroll
-      for (int jt = 0; jt < CH; ++jt) {
-        x0 = fmaxf(x0, fmaxf(s[jt][0], s[jt][1]));
-        x1 = fmaxf(x1, fmaxf(s[jt][2], s[jt][3]));
-      }
-      x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
-      x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
-      const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);        // finite: every chunk holds a valid key
-      if (c > 0) {
-        const float f0 = ex2(m0 - n0), f1 = ex2(m1 - n1);
-        l0 *= f0; l1 *= f1;
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          om[d][0] *= f0; om[d][1] *= f0; ox[d][0] *= f0; ox[d][1] *= f0;
-          om[d][2] *= f1; om[d][3] *= f1; ox[d][2] *= f1; ox[d][3] *= f1;
-        }
-      }
-      m0 = n0; m1 = n1;
-      // ---- O += P V ----
-#pragma unroll
-      for (int jt = 0; jt < CH; ++jt) {
-        const float p0 = ex2(s[jt][0] - m0), p1 = ex2(s[jt][1] - m0), p2 = ex2(s[jt][2] - m1), p3 = ex2(s[jt][3] - m1);
-        l0 += p0 + p1; l1 += p2 + p3;
-        // A fragment: column t <- key 2t, column t+4 <- key 2t+1 (the V pairs follow the same order)
-        uint32_t ph[4], pl[4];
-        ph[0] = __float_as_uint(p0) & 0xffffe000u; ph[1] = __float_as_uint(p2) & 0xffffe000u;
-        ph[2] = __float_as_uint(p1) & 0xffffe000u; ph[3] = __float_as_uint(p3) & 0xffffe000u;
-        pl[0] = __float_as_uint(p0 - __uint_as_float(ph[0])) & 0xffffe000u;
-        pl[1] = __float_as_uint(p2 - __uint_as_float(ph[1])) & 0xffffe000u;
-        pl[2] = __float_as_uint(p1 - __uint_as_float(ph[2])) & 0xffffe000u;
-        pl[3] = __float_as_uint(p3 - __uint_as_float(ph[3])) & 0xffffe000u;
-        const uint2* vt = vr + jt * 4 * VSTR;
-        const uint2 vh0 = vt[0], vh1 = vt[8], vl0 = vt[16], vl1 = vt[24];
-        mma_tf32(om[0], ph, vh0);
-        mma_tf32(om[1], ph, vh1);
-        mma_tf32(ox[0], pl, vh0);
-        mma_tf32(ox[1], pl, vh1);
-        mma_tf32(ox[0], ph, vl0);
-        mma_tf32(ox[1], ph, vl1);
-      }
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      if (r0 < n)
-        *reinterpret_cast<float2*>(heads + ((size_t)b * n + r0) * D + h * HD + d * 8 + 2 * t) =
-            make_float2((om[d][0] + ox[d][0]) * i0, (om[d][1] + ox[d][1]) * i0);
-      if (r1 < n)
-        *reinterpret_cast<float2*>(heads + ((size_t)b * n + r1) * D + h * HD + d * 8 + 2 * t) =
-            make_float2((om[d][2] + ox[d][2]) * i1, (om[d][3] + ox[d][3]) * i1);
-    }
+    float out[2][4];
+    attend<CH>(ksp + g * KSTR + t, vsp + t * VSTR + g, qhi, qlo, n, nchunk, t, out);
+    store_rows(heads + (size_t)b * n * D + h * HD, n, r0, t, out);
   }
 }
 
 template <int CH, int MAXT, int MINB>
-int launch_ch2(const float* qkv, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
+int launch_uniform(const float* qkv, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
   const int npad = ceil_div(n, 8 * CH) * 8 * CH;
   const size_t smem = (size_t)hpc * lane_bytes(npad);
   static size_t smem_set = 0;
@@ -235,13 +387,31 @@ int launch_ch2(const float* qkv, int B, int n, int hpc, int mt, float* heads, cu
   return AGH_OK;
 }
 
-// CTAs of up to 8 warps (N <= 127) may use up to 128 registers; larger graphs need up to 19 warps per CTA.
+template <int CH, int MAXT, int MINB>
+int launch_ws(const float* qkv, int B, int n, int mt, float* heads, cudaStream_t st) {
+  const int npad = ceil_div(n, 8 * CH) * 8 * CH;
+  const size_t smem = ws_smem_bytes(n, npad);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    AGH_CUDA(cudaFuncSetAttribute(mha_ws_kernel<CH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  mha_ws_kernel<CH, MAXT, MINB><<<B, (mt + 1) * 32, smem, st>>>(qkv, n, mt, heads);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+// CTAs of up to 8 warps (N <= 111 with the producer warp) may use up to 128 registers; larger graphs need up to 20.
 template <int CH>
 int launch_ch(const float* qkv, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
-  static const int minb = getenv("AGH_MHA_MINB") ? atoi(getenv("AGH_MHA_MINB")) : 2;
-  if (hpc * mt <= 8 && minb == 3) return launch_ch2<CH, 256, 3>(qkv, B, n, hpc, mt, heads, st);
-  if (hpc * mt <= 8) return launch_ch2<CH, 256, 2>(qkv, B, n, hpc, mt, heads, st);
-  return launch_ch2<CH, MHA_MAX_THREADS, 1>(qkv, B, n, hpc, mt, heads, st);
+  static const bool no_ws = getenv("AGH_MHA_WS") != nullptr && atoi(getenv("AGH_MHA_WS")) == 0;
+  const int npad = ceil_div(n, 8 * CH) * 8 * CH;
+  if (!no_ws && hpc == 1 && ws_smem_bytes(n, npad) <= 227 * 1024) {
+    if (mt + 1 <= 8) return launch_ws<CH, 256, 2>(qkv, B, n, mt, heads, st);
+    return launch_ws<CH, MHA_MAX_THREADS, 1>(qkv, B, n, mt, heads, st);
+  }
+  if (hpc * mt <= 8) return launch_uniform<CH, 256, 2>(qkv, B, n, hpc, mt, heads, st);
+  return launch_uniform<CH, MHA_MAX_THREADS, 1>(qkv, B, n, hpc, mt, heads, st);
 }
 
 }  // namespace
@@ -250,7 +420,7 @@ int launch_mha_mma(const float* qkv, int B, int n, float* heads, cudaStream_t st
   const int mt = ceil_div(n, 16);
   int hpc = 1;
   while (hpc < H && 2 * hpc * mt <= 8) hpc *= 2;                 // about 8 warps per CTA for small graphs
-  AGH_CHECK_ARG(hpc * mt * 32 <= MHA_MAX_THREADS);
+  AGH_CHECK_ARG((hpc * mt + 1) * 32 <= MHA_MAX_THREADS);
   // chunk length: least padded work (about 60 instructions per key fragment, 60 per chunk for the rescale)
   const int ntile = ceil_div(n, 8);
   int best = 8, best_cost = 1 << 30;
@@ -258,7 +428,6 @@ int launch_mha_mma(const float* qkv, int B, int n, float* heads, cudaStream_t st
     const int chunks = ceil_div(ntile, ch), cost = chunks * ch * 60 + chunks * 60;
     if (cost < best_cost) { best = ch; best_cost = cost; }
   }
-  if (getenv("AGH_MHA_CH")) best = atoi(getenv("AGH_MHA_CH"));
   switch (best) {
     case 3: return launch_ch<3>(qkv, B, n, hpc, mt, heads, st);
     case 4: return launch_ch<4>(qkv, B, n, hpc, mt, heads, st);
