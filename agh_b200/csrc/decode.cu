@@ -94,7 +94,7 @@ enum { RES_V = 1, RES_L = 2, RES_P = 4 };
 
 struct DecodeSmem {
   // byte offsets into dynamic shared memory
-  size_t V, L, P, twr, dur, twl, dem, crd, dcur, z, serve, o, qb, wc, wt, red, mw, bar, total;
+  size_t V, L, P, twr, dur, twl, dem, crd, dcur, z, serve, o, qb, wc, wt, red, mw, idx, bar, total;
 };
 
 __host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int res) {
@@ -111,6 +111,7 @@ __host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int res
   s.o = take(D * 4); s.qb = take(D * 4); s.wc = 0; s.wt = 0;       // qb slot holds the step's query vector
   s.red = take(8 * 4 * 4);
   s.mw = take(16 * 4);
+  s.idx = take(npad * 2);                       // compact list of the step's feasible nodes (u16)
   s.bar = take(16);
   s.total = off;
   return s;
@@ -135,6 +136,9 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   const DecodeSmem L = decode_smem_layout(n, NPL, RES);
   constexpr int NPAD = NPL * 32;
   constexpr int MPT = (NPAD + 255) / 256;                 // mask nodes per thread (node = tid + 256 k)
+  // large graphs walk a compact list of the feasible nodes in the value / logit phases (measured: N = 300 +41 %,
+  // N = 200 +3 %, N <= 100 -4 %: there the fully unrolled fixed mapping wins)
+  constexpr bool COMPACT = NPL > 4;
 
   float* sV = reinterpret_cast<float*>(smem + L.V);
   float* sL = reinterpret_cast<float*>(smem + L.L);
@@ -151,6 +155,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   float* s_q = reinterpret_cast<float*>(smem + L.qb);        // query of the current step, written by threads 0..127
   float* s_red = reinterpret_cast<float*>(smem + L.red);
   uint32_t* s_mw = reinterpret_cast<uint32_t*>(smem + L.mw);
+  uint16_t* s_idx = reinterpret_cast<uint16_t*>(smem + L.idx);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
   const float* gkeys = a.keys + (size_t)kb * 3 * n * KS;
@@ -290,6 +295,25 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       feas |= (p == 0) ? (~mw[p] & 0xfffffffeu) : ~mw[p];
     }
     mw[0] = (mw[0] & 0xfffffffeu) | ((prev == 0 && feas != 0u) ? 1u : 0u);      // depot: state_agh.py:173
+    int nfeas = 0;
+    if constexpr (COMPACT) {
+      // Feasibility is sparse (about a quarter of the nodes on average, SURVEY 3.5 workloads): the value and logit
+      // phases below walk a COMPACT list of the feasible nodes instead of all n.  Every warp builds the same list
+      // (ballot order = increasing node index) and reads it back after its own __syncwarp; masked nodes get their
+      // -inf log-prob slot here.
+  #pragma unroll
+      for (int p = 0; p < NPL; ++p) {
+        const uint32_t fw = ~mw[p];
+        if ((fw >> lane) & 1u) s_idx[nfeas + __popc(fw & ((1u << lane) - 1u))] = (uint16_t)(32 * p + lane);
+        nfeas += __popc(fw);
+      }
+  #pragma unroll
+      for (int k = 0; k < MPT; ++k) {
+        const int j = tid + 256 * k;
+        if (j < n && ((pick_word<NPL>(mw, warp + 8 * k) >> lane) & 1u)) s_z[j] = -CUDART_INF_F;
+      }
+      __syncwarp();
+    }
     if (warp == 0) {
       if (a.mask_dump != nullptr && lane < nwords) a.mask_dump[(trow + t) * nwords + lane] = pick_word<NPL>(mw, lane);
       if (lane == 0) {
@@ -310,7 +334,8 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         const float4 qv = q4[i];
 #pragma unroll
         for (int p = 0; p < NPL; ++p)
-          s[p] = dot4(qv, make_float4(kreg[p][4 * i], kreg[p][4 * i + 1], kreg[p][4 * i + 2], kreg[p][4 * i + 3]), s[p]);
+          if (!COMPACT || mw[p] != 0xffffffffu)         // warp-uniform: a fully masked 32-node word needs no scores
+            s[p] = dot4(qv, make_float4(kreg[p][4 * i], kreg[p][4 * i + 1], kreg[p][4 * i + 2], kreg[p][4 * i + 3]), s[p]);
       }
     }
 
@@ -336,18 +361,43 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     float acc[HD];
 #pragma unroll
     for (int k = 0; k < HD; ++k) acc[k] = 0.f;
-#pragma unroll
-    for (int p = 0; p < NPL; ++p) {
-      const int j = lane + 32 * p;
-      if (j < n) {
-        const float4* vr = reinterpret_cast<const float4*>(Vm + (size_t)j * KS);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 v = vr[swz(h * 4 + i, j)];
-          acc[4 * i + 0] = fmaf(e[p], v.x, acc[4 * i + 0]);
-          acc[4 * i + 1] = fmaf(e[p], v.y, acc[4 * i + 1]);
-          acc[4 * i + 2] = fmaf(e[p], v.z, acc[4 * i + 2]);
-          acc[4 * i + 3] = fmaf(e[p], v.w, acc[4 * i + 3]);
+    if constexpr (COMPACT) {
+      for (int c0 = 0; c0 < nfeas; c0 += 32) {          // lane <-> compact slot; masked nodes have weight 0 and are skipped
+        const bool valid = c0 + lane < nfeas;
+        const int j = valid ? (int)s_idx[c0 + lane] : 0;
+        const int src = j & 31, pj = j >> 5;
+        float ev = 0.f;                                 // weight of node j: register e[pj] of lane src
+  #pragma unroll
+        for (int p = 0; p < NPL; ++p) {
+          const float v = __shfl_sync(0xffffffffu, e[p], src);
+          ev = (pj == p) ? v : ev;
+        }
+        if (valid) {
+          const float4* vr = reinterpret_cast<const float4*>(Vm + (size_t)j * KS);
+  #pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = vr[swz(h * 4 + i, j)];
+            acc[4 * i + 0] = fmaf(ev, v.x, acc[4 * i + 0]);
+            acc[4 * i + 1] = fmaf(ev, v.y, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(ev, v.z, acc[4 * i + 2]);
+            acc[4 * i + 3] = fmaf(ev, v.w, acc[4 * i + 3]);
+          }
+        }
+      }
+    } else {
+  #pragma unroll
+      for (int p = 0; p < NPL; ++p) {
+        const int j = lane + 32 * p;
+        if (j < n) {
+          const float4* vr = reinterpret_cast<const float4*>(Vm + (size_t)j * KS);
+  #pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = vr[swz(h * 4 + i, j)];
+            acc[4 * i + 0] = fmaf(e[p], v.x, acc[4 * i + 0]);
+            acc[4 * i + 1] = fmaf(e[p], v.y, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(e[p], v.z, acc[4 * i + 2]);
+            acc[4 * i + 3] = fmaf(e[p], v.w, acc[4 * i + 3]);
+          }
         }
       }
     }
@@ -379,66 +429,126 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     }
     __syncthreads();   // (A) o complete
 
-    // (7) logits for 16 nodes per warp and pass; lanes 0-15 take features 0..63, lanes 16-31 64..127
-    const int half = lane >> 4, jj = lane & 15;
-    constexpr int NPASS = (NPL * 32 + 127) / 128;
-    float zp[NPASS];
-    // selection score as an order-preserving integer key, so the arg-max is two warp REDUX operations
-    int best_key = (int)0x80000000;
-    int best_j = 0x7fffffff;
-#pragma unroll
-    for (int ps = 0; ps < NPASS; ++ps) {
-      const int j = ps * 128 + warp * 16 + jj;
-      float u = 0.f;
-      if (j < n) {
-        const float4* lr = reinterpret_cast<const float4*>(Lm + (size_t)j * KS);
-        const float4* o4 = reinterpret_cast<const float4*>(s_o + half * 64);
-        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          u0 = dot4(o4[i], lr[swz(half * 16 + i, j)], u0);
-          u1 = dot4(o4[i + 1], lr[swz(half * 16 + i + 1, j)], u1);
-          u2 = dot4(o4[i + 2], lr[swz(half * 16 + i + 2, j)], u2);
-          u3 = dot4(o4[i + 3], lr[swz(half * 16 + i + 3, j)], u3);
+    if constexpr (COMPACT) {
+      // (7) logits of the FEASIBLE nodes: 4 nodes per warp and pass, 8 lanes per node.  Lane fg of a node takes the
+      //     16-byte chunks {fg, fg+8, fg+16, fg+24} of its LK' row: the 8 lanes of a quarter-warp read one whole
+      //     swizzled 128-byte group (conflict-free) and the matching chunks of o are a broadcast across the 4 nodes.
+      const int ns = lane >> 3, fg = lane & 7;
+      // selection score as an order-preserving integer key, so the arg-max is two warp REDUX operations
+      int best_key = (int)0x80000000;
+      int best_j = 0x7fffffff;
+      float wm = shift, ws = 0.f;
+      for (int c0 = warp * 4; c0 < nfeas; c0 += 32) {
+        const bool valid = c0 + ns < nfeas;
+        const int j = valid ? (int)s_idx[c0 + ns] : 0;
+        float u = 0.f;
+        if (valid) {
+          const float4* lr = reinterpret_cast<const float4*>(Lm + (size_t)j * KS);
+          const float4* o4 = reinterpret_cast<const float4*>(s_o);
+          const int sw = (fg ^ j) & 7;
+          const float u0 = dot4(o4[fg], lr[sw], 0.f), u1 = dot4(o4[8 + fg], lr[8 + sw], 0.f);
+          const float u2 = dot4(o4[16 + fg], lr[16 + sw], 0.f), u3 = dot4(o4[24 + fg], lr[24 + sw], 0.f);
+          u = (u0 + u1) + (u2 + u3);
         }
-        u = (u0 + u1) + (u2 + u3);
+        u += __shfl_xor_sync(0xffffffffu, u, 1);
+        u += __shfl_xor_sync(0xffffffffu, u, 2);
+        u += __shfl_xor_sync(0xffffffffu, u, 4);
+        if (valid && fg == 0) {
+          float z = 10.0f * tanhf(u);                               // attention_model.py:580
+          if (!unit_temp) z = __fdiv_rn(z, a.temp);                 // :447
+          s_z[j] = z;
+          float sc = z;
+          if (a.inject_logp != nullptr) {
+            sc = expf(__ldg(a.inject_logp + (trow + t) * n + j));   // argmax(exp(log_p)), :333,:377
+          } else if (a.mode == AGH_SAMPLING) {
+            sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
+          }
+          if (fixed_shift) ws += expf(z - shift);
+          int key = __float_as_int(sc);
+          key ^= (key >> 31) & 0x7fffffff;                          // monotone float -> int map
+          if (key > best_key) { best_key = key; best_j = j; }       // strict: the list is in index order, first index wins ties
+        }
       }
-      u += __shfl_xor_sync(0xffffffffu, u, 16);
-      const bool mj = (j >= n) || ((pick_word<NPL>(mw, j >> 5) >> (j & 31)) & 1u);
-      float z = -CUDART_INF_F;
-      if (!mj) {
-        z = 10.0f * tanhf(u);                                   // attention_model.py:580
-        if (!unit_temp) z = __fdiv_rn(z, a.temp);               // :447
+      if (!fixed_shift) {                                           // cold temperatures: exact max-merging log-sum-exp
+        __syncwarp();
+        wm = -CUDART_INF_F;
+        for (int c0 = warp * 4; c0 < nfeas; c0 += 32)
+          if (c0 + ns < nfeas && fg == 0) wm = fmaxf(wm, s_z[s_idx[c0 + ns]]);
+  #pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+        for (int c0 = warp * 4; c0 < nfeas; c0 += 32)
+          if (c0 + ns < nfeas && fg == 0) ws += expf(s_z[s_idx[c0 + ns]] - wm);
       }
-      if (half == 0 && j < n) s_z[j] = z;
-      float sc = z;
-      if (a.inject_logp != nullptr) {
-        sc = (j < n) ? expf(__ldg(a.inject_logp + (trow + t) * n + j)) : -CUDART_INF_F;   // argmax(exp(log_p)), :333,:377
-      } else if (a.mode == AGH_SAMPLING && !mj) {
-        sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
+  #pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, off);
+      {
+        const int kmax = __reduce_max_sync(0xffffffffu, best_key);
+        const int jmin = __reduce_min_sync(0xffffffffu, best_key == kmax ? best_j : 0x7fffffff);
+        if (lane == 0)
+          *reinterpret_cast<float4*>(s_red + warp * 4) = make_float4(ws, __int_as_float(kmax), __int_as_float(jmin), wm);
       }
-      zp[ps] = (half == 0) ? z : -CUDART_INF_F;
-      int key = __float_as_int(sc);
-      key ^= (key >> 31) & 0x7fffffff;                          // monotone float -> int map
-      if (half == 0 && key > best_key) { best_key = key; best_j = j; }     // strict: first index wins ties
-    }
-    float wm = shift, ws = 0.f;
-    if (!fixed_shift) {
-      wm = -CUDART_INF_F;
-#pragma unroll
-      for (int ps = 0; ps < NPASS; ++ps) wm = fmaxf(wm, zp[ps]);
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
-    }
-#pragma unroll
-    for (int ps = 0; ps < NPASS; ++ps) ws += (zp[ps] == -CUDART_INF_F) ? 0.f : expf(zp[ps] - wm);
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, off);
-    {
-      const int kmax = __reduce_max_sync(0xffffffffu, best_key);
-      const int jmin = __reduce_min_sync(0xffffffffu, best_key == kmax ? best_j : 0x7fffffff);
-      if (lane == 0)
-        *reinterpret_cast<float4*>(s_red + warp * 4) = make_float4(ws, __int_as_float(kmax), __int_as_float(jmin), wm);
+    } else {
+      // (7) logits for 16 nodes per warp and pass; lanes 0-15 take features 0..63, lanes 16-31 64..127
+      const int half = lane >> 4, jj = lane & 15;
+      constexpr int NPASS = (NPL * 32 + 127) / 128;
+      float zp[NPASS];
+      // selection score as an order-preserving integer key, so the arg-max is two warp REDUX operations
+      int best_key = (int)0x80000000;
+      int best_j = 0x7fffffff;
+  #pragma unroll
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int j = ps * 128 + warp * 16 + jj;
+        float u = 0.f;
+        if (j < n) {
+          const float4* lr = reinterpret_cast<const float4*>(Lm + (size_t)j * KS);
+          const float4* o4 = reinterpret_cast<const float4*>(s_o + half * 64);
+          float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+  #pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            u0 = dot4(o4[i], lr[swz(half * 16 + i, j)], u0);
+            u1 = dot4(o4[i + 1], lr[swz(half * 16 + i + 1, j)], u1);
+            u2 = dot4(o4[i + 2], lr[swz(half * 16 + i + 2, j)], u2);
+            u3 = dot4(o4[i + 3], lr[swz(half * 16 + i + 3, j)], u3);
+          }
+          u = (u0 + u1) + (u2 + u3);
+        }
+        u += __shfl_xor_sync(0xffffffffu, u, 16);
+        const bool mj = (j >= n) || ((pick_word<NPL>(mw, j >> 5) >> (j & 31)) & 1u);
+        float z = -CUDART_INF_F;
+        if (!mj) {
+          z = 10.0f * tanhf(u);                                   // attention_model.py:580
+          if (!unit_temp) z = __fdiv_rn(z, a.temp);               // :447
+        }
+        if (half == 0 && j < n) s_z[j] = z;
+        float sc = z;
+        if (a.inject_logp != nullptr) {
+          sc = (j < n) ? expf(__ldg(a.inject_logp + (trow + t) * n + j)) : -CUDART_INF_F;   // argmax(exp(log_p)), :333,:377
+        } else if (a.mode == AGH_SAMPLING && !mj) {
+          sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
+        }
+        zp[ps] = (half == 0) ? z : -CUDART_INF_F;
+        int key = __float_as_int(sc);
+        key ^= (key >> 31) & 0x7fffffff;                          // monotone float -> int map
+        if (half == 0 && key > best_key) { best_key = key; best_j = j; }     // strict: first index wins ties
+      }
+      float wm = shift, ws = 0.f;
+      if (!fixed_shift) {
+        wm = -CUDART_INF_F;
+  #pragma unroll
+        for (int ps = 0; ps < NPASS; ++ps) wm = fmaxf(wm, zp[ps]);
+  #pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+      }
+  #pragma unroll
+      for (int ps = 0; ps < NPASS; ++ps) ws += (zp[ps] == -CUDART_INF_F) ? 0.f : expf(zp[ps] - wm);
+  #pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, off);
+      {
+        const int kmax = __reduce_max_sync(0xffffffffu, best_key);
+        const int jmin = __reduce_min_sync(0xffffffffu, best_key == kmax ? best_j : 0x7fffffff);
+        if (lane == 0)
+          *reinterpret_cast<float4*>(s_red + warp * 4) = make_float4(ws, __int_as_float(kmax), __int_as_float(jmin), wm);
+      }
     }
     __syncthreads();   // (B) per-warp partials complete
 
