@@ -346,8 +346,13 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       s[p] = ((mw[p] >> lane) & 1u) ? -CUDART_INF_F : s[p];
       mx = fmaxf(mx, s[p]);
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    {   // warp max as ONE integer REDUX on the order-preserving key of the float (the map is its own inverse)
+      int key = __float_as_int(mx);
+      key ^= (key >> 31) & 0x7fffffff;
+      key = __reduce_max_sync(0xffffffffu, key);
+      key ^= (key >> 31) & 0x7fffffff;
+      mx = __int_as_float(key);
+    }
     float e[NPL], esum = 0.f;
 #pragma unroll
     for (int p = 0; p < NPL; ++p) {
