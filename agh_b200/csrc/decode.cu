@@ -245,13 +245,17 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   const bool fixed_shift = a.temp >= 0.25f;
   const float shift = __fdiv_rn(10.0f, a.temp);
 
-  while (replay ? (t < a.replay_steps) : (nvis < n)) {
-    const int cprev = s_crd[prev];
-    float* dc = s_dcur + (t & 1) * NPAD;
-    // (1) distance from the current location to the node(s) this thread masks
-    float ddm[MPT];
+  // (1) distance from the current location to the node(s) this thread masks, and this thread's component of the
+  //     current node's P_sc row when that table is not in shared memory: both come through L2, so they are requested
+  //     as soon as the node is known (end of the previous step) and land during the log-likelihood / state update
+  float ddm[MPT];
 #pragma unroll
-    for (int k = 0; k < MPT; ++k) ddm[k] = (tid + 256 * k < n) ? __ldg(a.distance + NODE_SIZE * cprev + cjm[k]) : 0.f;
+  for (int k = 0; k < MPT; ++k) ddm[k] = (tid + 256 * k < n) ? __ldg(a.distance + NODE_SIZE * s_crd[0] + cjm[k]) : 0.f;
+  float pv_r = 0.f;
+  if (!(RES & RES_P) && tid < D) pv_r = __ldg(Pm + tid);
+
+  while (replay ? (t < a.replay_steps) : (nvis < n)) {
+    float* dc = s_dcur + (t & 1) * NPAD;
 
     // (2) query for my head: attention_model.py:432-435,510-522
     const float rem = 1.0f - used;
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     }
     // one component of the query per thread (threads 0..127), published through shared memory
     if (tid < D) {
-      const float pv = (RES & RES_P) ? Pm[(size_t)prev * D + tid] : __ldg(Pm + (size_t)prev * D + tid);
+      const float pv = (RES & RES_P) ? Pm[(size_t)prev * D + tid] : pv_r;
       s_q[tid] = fmaf(wt_r, tf, fmaf(wc_r, rem, qb_r + pv));
     }
 
@@ -361,6 +365,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, off);
+    const float inv_esum = __frcp_rn(esum);          // off the critical path of the butterfly below
 
     // (6) o_h = sum_j a_j V_jh, butterfly transpose-reduce over the 32 lanes
     float acc[HD];
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       }
       r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
       // lane now owns element lane >> 1 of o_h
-      if ((lane & 1) == 0) s_o[h * HD + (lane >> 1)] = __fdiv_rn(r1, esum);
+      if ((lane & 1) == 0) s_o[h * HD + (lane >> 1)] = r1 * inv_esum;
     }
     __syncthreads();   // (A) o complete
 
@@ -581,6 +586,12 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     }
     const float logS = logf(S);
     if (replay) sel = (int)a.actions[trow + t];
+    {   // next step's distance row / P_sc component (see (1))
+      const int cnext = s_crd[sel];
+#pragma unroll
+      for (int k = 0; k < MPT; ++k) ddm[k] = (tid + 256 * k < n) ? __ldg(a.distance + NODE_SIZE * cnext + cjm[k]) : 0.f;
+      if (!(RES & RES_P) && tid < D) pv_r = __ldg(Pm + (size_t)sel * D + tid);
+    }
     const float g_z = s_z[sel];
     const float lp = (g_z - M) - logS;
     ll += lp;
