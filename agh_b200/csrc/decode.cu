@@ -94,7 +94,7 @@ enum { RES_V = 1, RES_L = 2, RES_P = 4 };
 
 struct DecodeSmem {
   // byte offsets into dynamic shared memory
-  size_t V, L, P, twr, dur, twl, dem, crd, dcur, z, serve, o, qb, wc, wt, red, mw, idx, bar, total;
+  size_t V, L, P, twr, dur, twl, dem, crd, dcur, z, serve, o, qb, wc, wt, red, mw, idx, fin, bar, total;
 };
 
 __host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int res) {
@@ -112,6 +112,7 @@ __host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int res
   s.red = take(8 * 4 * 4);
   s.mw = take(16 * 4);
   s.idx = take(npad * 2);                       // compact list of the step's feasible nodes (u16)
+  s.fin = take(npad * 8);                       // finish time of every node if it were served next (f64)
   s.bar = take(16);
   s.total = off;
   return s;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   float* s_red = reinterpret_cast<float*>(smem + L.red);
   uint32_t* s_mw = reinterpret_cast<uint32_t*>(smem + L.mw);
   uint16_t* s_idx = reinterpret_cast<uint16_t*>(smem + L.idx);
+  double* s_fin = reinterpret_cast<double*>(smem + L.fin);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
   const float* gkeys = a.keys + (size_t)kb * 3 * n * KS;
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         const float tt = __fdiv_rn(ddm[k], 110.0f);
         const double fin = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)twlm[k]), durm[k]);
         mj = vis[k] | cap | (fin > twrm[k]);
+        s_fin[j] = fin;      // exactly the new cur_free_time if j is served next (state_agh.py:117-121): reused by the update
       }
       const uint32_t word = __ballot_sync(0xffffffffu, mj);
       if (j < NPAD) {
@@ -603,8 +606,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     len = __fadd_rn(len, d);
     if (sel != 0) {
       used = __fadd_rn(used, s_dem[sel]);
-      const float tt = __fdiv_rn(d, 110.0f);
-      cft = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)s_twl[sel]), s_dur[sel]);
+      cft = s_fin[sel];      // = fmax(cft + d/110, tw_left[sel]) + duration[sel], evaluated by the node's own thread above
       ++nvis;
     } else {
       used = 0.f;
