@@ -244,7 +244,7 @@ def run_cuda(args):
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         # physical DRAM bytes per decode launch from the committed `ncu --set full` capture of this very workload
         traffic = None
-        tp = os.path.join(ROOT, 'profiles', 'r1d_decode_traffic.json')
+        tp = os.path.join(ROOT, 'profiles', 'r1f_decode_traffic.json')
         if os.path.exists(tp) and (N, B) == (100, 10000):
             traffic = json.load(open(tp))['traffic_bytes_per_launch']
         line = {
@@ -267,7 +267,7 @@ def run_cuda(args):
                          'instance_steps_per_launch': inst_steps_per_launch, 'launch_ms': dec_launch_ms,
                          'share_of_step': t_dec / ms_res,
                          'note': 'keys stay on chip (registers + shared memory) for all T steps, so the fraction exceeds 1: '
-                                 'physical DRAM traffic is the one-time staging only (profiles/r1d_decode_traffic.json)'},
+                                 'physical DRAM traffic is the one-time staging only (profiles/r1f_decode_traffic.json)'},
             'roofline_encoder': {'kernels': 'gemm_tc_kernel + mha_mma_kernel + init_embed (agh_encode, agh_precompute)',
                                  'bound': 'tensor', 'achieved': enc_tflops, 'peak': tflops, 'unit': 'TFLOP/s',
                                  'frac': enc_tflops / tflops, 'share_of_step': (t_enc + t_pre) / ms_res,
