@@ -106,6 +106,8 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import agh_oracle as O
+    # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to every rank)
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
     tb, W = O.Tables.load(), O.random_init_weights(1234)
     B = args.cpu_sample
     inst = make_batch(B, args.flights, 4321)
@@ -303,7 +305,7 @@ def main():
     ap.add_argument('--flights', type=int, default=100)
     ap.add_argument('--batch', type=int, default=10000, help='instances per GPU per step')
     ap.add_argument('--cpu-sample', type=int, default=128, help='--impl reference: instances per step')
-    ap.add_argument('--cpu-baseline-sample', type=int, default=256)
+    ap.add_argument('--cpu-baseline-sample', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
