@@ -18,7 +18,12 @@
 //       s_hj = q_h . K'_jh ; a_h = softmax_j(s_h | mask) ; o_h = sum_j a_hj V_jh
 //       u_j = 10 tanh(o . LK'_j) ; log_p = log_softmax(u / temp | mask)
 //   * 8 warps = 8 heads for the glimpse (warp-local softmax, no block sync), then 16 nodes per
-//     warp for the logits; two __syncthreads per step.
+//     warp for the logits; three __syncthreads per step.  The kernel is bound by the latency of this
+//     per-step dependency chain, so the chain is kept short: integer REDUX for every max / arg-max, the
+//     next step's L2 reads (distance row, P_sc component) issued the moment the node is selected, the
+//     selected node's finish time read back from the thread that evaluated it for the mask.
+//   * graphs with more than 127 nodes walk a compact list of the step's feasible nodes in the value
+//     and logit phases (feasibility is sparse: about 30 % of the nodes on average).
 //   * feasibility mask and state transition follow the reference's mixed f32/f64 arithmetic
 //     exactly (SURVEY.md section 8a numerics contract): f32 table lookup, f32 IEEE division by
 //     110, f64 time accumulation, f32 capacity.

@@ -17,10 +17,11 @@
 // follow the same key order, so no shuffle is needed between the two products.
 //
 // Two kernels share that inner routine:
-//  * mha_ws_kernel (default when it fits): warp-specialised.  One producer warp streams the raw Q_h|K_h|V_h rows of
-//    the next head with cp.async.bulk (mbarrier complete_tx) and converts K_h, V_h into the fragment-ordered buffer
-//    of a two-deep ring; the compute warps only wait on the ring's full/empty mbarriers, so the HMMA pipe is never
-//    idled by a staging phase or a CTA-wide barrier.
+//  * mha_ws_kernel (default when it fits): warp-specialised.  One producer warp streams the raw K_h|V_h rows of the
+//    next head with 16-byte cp.async into a double-buffered raw buffer (64-byte cp.async.bulk copies, 303 per head,
+//    were 2x slower to issue) and converts them into the fragment-ordered buffer of a two-deep ring; the compute
+//    warps read their Q fragments from global memory one head ahead and otherwise only wait on the ring's
+//    full/empty mbarriers, so the HMMA pipe is never idled by a staging phase or a CTA-wide barrier.
 //  * mha_mma_kernel: every warp stages and computes (cp.async prefetch of the next head, two __syncthreads per
 //    head); used for small graphs (several heads per CTA) and when the ring does not fit in shared memory.
 #include "common.cuh"
@@ -34,7 +35,6 @@ namespace {
 
 constexpr int RAWS = 52;          // mha_mma_kernel raw row stride in floats: Q 16 | K 16 | V 16 | pad 4
 constexpr int KVS = 36;           // mha_ws_kernel raw K|V row stride in floats: K 16 | V 16 | pad 4
-constexpr int QS = 20;            // mha_ws_kernel raw Q row stride in floats: Q 16 | pad 4
 constexpr int KSTR = 20;          // split K row (one key): 8 hi pairs, 8 lo pairs, 4 pad
 constexpr int VSTR = 36;          // split V row (two keys): 16 hi pairs, 16 lo pairs, 4 pad
 constexpr int MHA_MAX_THREADS = 640;
@@ -48,19 +48,6 @@ __device__ __forceinline__ void split_rn(float x, uint32_t& hi, uint32_t& lo) {
   hi = tf32_rn(x);
   lo = tf32_rn(x - __uint_as_float(hi));
 }
-// hi = x truncated to TF32, lo = (x - hi) truncated: 3 operations instead of 5; |x - hi - lo| <= 2^-21 |x|
-__device__ __forceinline__ void split_tr(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
-}
-#ifndef AGH_MHA_SPLIT_TRUNC
-#define AGH_MHA_SPLIT_TRUNC 0
-#endif
-#if AGH_MHA_SPLIT_TRUNC
-#define SPLIT_KV split_tr
-#else
-#define SPLIT_KV split_rn
-#endif
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -78,9 +65,6 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
@@ -97,16 +81,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
 // (a_i, b_i), i = 0..3  ->  4 hi pairs at dst[0..3], 4 lo pairs at dst[lo_off..lo_off+3]
 __device__ __forceinline__ void store_pairs(uint2* dst, int lo_off, const float4 a, const float4 b) {
   uint32_t ah[4], al[4], bh[4], bl[4];
-  SPLIT_KV(a.x, ah[0], al[0]); SPLIT_KV(a.y, ah[1], al[1]); SPLIT_KV(a.z, ah[2], al[2]); SPLIT_KV(a.w, ah[3], al[3]);
-  SPLIT_KV(b.x, bh[0], bl[0]); SPLIT_KV(b.y, bh[1], bl[1]); SPLIT_KV(b.z, bh[2], bl[2]); SPLIT_KV(b.w, bh[3], bl[3]);
+  split_rn(a.x, ah[0], al[0]); split_rn(a.y, ah[1], al[1]); split_rn(a.z, ah[2], al[2]); split_rn(a.w, ah[3], al[3]);
+  split_rn(b.x, bh[0], bl[0]); split_rn(b.y, bh[1], bl[1]); split_rn(b.z, bh[2], bl[2]); split_rn(b.w, bh[3], bl[3]);
   uint4* d = reinterpret_cast<uint4*>(dst);
   d[0] = make_uint4(ah[0], bh[0], ah[1], bh[1]);
   d[1] = make_uint4(ah[2], bh[2], ah[3], bh[3]);
