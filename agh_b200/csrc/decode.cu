@@ -117,7 +117,7 @@ __host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int res
   s.red = take(8 * 4 * 4);
   s.mw = take(16 * 4);
   s.idx = take(npad * 2);                       // compact list of the step's feasible nodes (u16)
-  s.fin = take(npad * 8);                       // finish time of every node if it were served next (f64)
+  s.fin = take(2 * npad * 8);                   // finish time of every node if it were served next (f64), double-buffered
   s.bar = take(16);
   s.total = off;
   return s;
@@ -263,6 +263,9 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
 
   while (replay ? (t < a.replay_steps) : (nvis < n)) {
     float* dc = s_dcur + (t & 1) * NPAD;
+    // like dc, double-buffered by step parity: a fast warp's writes of step t+1 must not overtake a slow warp's
+    // reads of step t (no barrier separates a step's selection phase from the next step's mask phase)
+    double* fin_t = s_fin + (t & 1) * NPAD;
 
     // (2) query for my head: attention_model.py:432-435,510-522
     const float rem = 1.0f - used;
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         const float tt = __fdiv_rn(ddm[k], 110.0f);
         const double fin = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)twlm[k]), durm[k]);
         mj = vis[k] | cap | (fin > twrm[k]);
-        s_fin[j] = fin;      // exactly the new cur_free_time if j is served next (state_agh.py:117-121): reused by the update
+        fin_t[j] = fin;      // exactly the new cur_free_time if j is served next (state_agh.py:117-121): reused by the update
       }
       const uint32_t word = __ballot_sync(0xffffffffu, mj);
       if (j < NPAD) {
@@ -592,7 +595,6 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       for (int off = 4; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
       S = __shfl_sync(0xffffffffu, part, 0);
     }
-    const float logS = logf(S);
     if (replay) sel = (int)a.actions[trow + t];
     {   // next step's distance row / P_sc component (see (1))
       const int cnext = s_crd[sel];
@@ -601,6 +603,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       if (!(RES & RES_P) && tid < D) pv_r = __ldg(Pm + (size_t)sel * D + tid);
     }
     const float g_z = s_z[sel];
+    const float logS = logf(S);
     const float lp = (g_z - M) - logS;
     ll += lp;
     if (a.logp_full != nullptr) {
@@ -611,7 +614,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     len = __fadd_rn(len, d);
     if (sel != 0) {
       used = __fadd_rn(used, s_dem[sel]);
-      cft = s_fin[sel];      // = fmax(cft + d/110, tw_left[sel]) + duration[sel], evaluated by the node's own thread above
+      cft = fin_t[sel];      // = fmax(cft + d/110, tw_left[sel]) + duration[sel], evaluated by the node's own thread above
       ++nvis;
     } else {
       used = 0.f;
