@@ -210,6 +210,22 @@ def test_shard_invariance(cuda_model):
     assert torch.equal(full, torch.cat((a, b), 0))
 
 
+@pytest.mark.parametrize('n', [50, 100, 200])
+def test_results_do_not_depend_on_timing(cuda_model, n):
+    """Race detector: every warp of a decode CTA keeps its own copy of the vehicle state, so an unsynchronised
+    shared-memory hand-off shows up as results that change with the timing.  A saturated GPU (two instances per SM,
+    thousands of CTAs), a lightly loaded one (a few CTAs) and a repeat must give bit-identical costs."""
+    base = {k: v[:1000] for k, v in make_instances(n).items()}
+    inst = {k: v.repeat(*([5] + [1] * (v.dim() - 1))) for k, v in base.items()}      # 5 x 1000 instances
+    B = inst['loc'].size(0)
+    first = _rollout(cuda_model, inst, bs=B)
+    again = _rollout(cuda_model, inst, bs=B)
+    assert torch.equal(first, again)
+    assert torch.equal(first[:1000], first[1000:2000])                  # identical instances, different CTAs / SMs
+    light = _rollout(cuda_model, {k: v[:48] for k, v in inst.items()}, bs=16)
+    assert torch.equal(first[:48], light)
+
+
 def test_get_costs_kernel(cuda_model, tables):
     from agh_b200 import AGH
     inst = {k: v[:64] for k, v in make_instances(20).items()}
