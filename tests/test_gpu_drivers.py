@@ -194,3 +194,25 @@ def test_level_batched_fleets_equal_sequential(cuda_model, n, B):
         assert torch.equal(a, b)
     for f in range(1, 11):
         assert torch.equal(seen[('seq', f)], seen[('lvl', f)])
+
+
+def test_edge_cases_empty_single_and_oversized(cuda_model):
+    """Empty dataset -> empty cost table; a single instance equals its row in a larger batch (ragged last batch
+    included); a graph beyond AGH_MAX_N is rejected loudly by the C ABI instead of being mis-computed."""
+    from agh_b200 import _lib, ops
+    from agh_b200.train import rollout
+    from agh_b200.problems.agh.problem_agh import generate_arrays
+    opts = types.SimpleNamespace(eval_batch_size=7, device=torch.device('cuda'), no_progress_bar=True)
+    empty = rollout(cuda_model, _dataset(20, 0), opts)
+    assert empty.shape == (0, 10)
+    many = rollout(cuda_model, _dataset(20, 23), opts)                   # batches of 7, 7, 7, 2
+    one = rollout(cuda_model, _dataset(20, 1), opts)
+    assert many.shape == (23, 10) and torch.equal(many[:1], one)
+    base = {k: v[:2] for k, v in make_instances(200).items()}            # 400 flights: two AGH-200 instances side by side
+    big = {k: torch.cat((v, v), dim=v.dim() - 1).contiguous().cuda() for k, v in base.items()}
+    with pytest.raises(_lib.AghError):
+        lv = big['arrival'].repeat(6, 1, 1).contiguous()
+        info = cuda_model.fleet_info
+        task = ops.fleet_task(big['loc'], big['type'], big['departure'], big['demand'], lv, 0, 1, info['duration'][1],
+                              info['next_duration'][0], nd_is_f32=False)
+        ops.encode(cuda_model.weight_blob(), task)
