@@ -8,8 +8,8 @@
 //
 // Data layout:
 //   * the instance's K' rows are loaded ONCE into registers (16 NPL per thread) and its V / LK' rows
-//     ([n][128] f32, chunk-swizzled, written by agh_precompute) are staged ONCE into shared memory with
-//     cp.async.bulk (TMA bulk copy, mbarrier completion); all stay on chip for all T steps.
+//     ([n][128] f32, plain rows written by agh_precompute) are staged ONCE into shared memory with
+//     cp.async.bulk (TMA bulk copy, mbarrier completion) and chunk-swizzled in place; all stay on chip for all T steps.
 //     P_sc = W_sc[:, :128] h (the node part of the step-context projection) is staged too when that
 //     does not cost a resident CTA.  At N = 100 this is 111 KB + 64 registers per instance, so TWO
 //     instances share an SM and hide each other's step latency; N = 300 streams V through L2.
@@ -123,7 +123,7 @@ __host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int res
   return s;
 }
 
-// Key rows are stored unpadded ([n][128] f32) with the 16-byte chunks of every aligned 8-chunk group
+// Key rows are held in shared memory unpadded ([n][128] f32) with the 16-byte chunks of every aligned 8-chunk group
 // XOR-swizzled by (node & 7): lanes that read the same logical chunk of 8 consecutive nodes hit 8
 // different bank groups, so every LDS.128 below is conflict-free without padding bytes.
 __device__ __forceinline__ int swz(int chunk, int node) { return (chunk & ~7) | ((chunk ^ node) & 7); }
@@ -165,7 +165,11 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   double* s_fin = reinterpret_cast<double*>(smem + L.fin);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
-  const float* gkeys = a.keys + (size_t)kb * 3 * n * KS;
+  // keys = [3][KB][n][128]: K', V, LK' as three plain row-major matrices (written by agh_precompute's GEMM epilogue)
+  const size_t KB = a.key_mod > 0 ? (size_t)a.key_mod : (size_t)a.B;
+  const float* gK = a.keys + (size_t)kb * n * KS;
+  const float* gV = a.keys + (KB + kb) * n * KS;
+  const float* gL = a.keys + (2 * KB + kb) * n * KS;
   const float* gpsc = a.psc + (size_t)kb * n * D;
 
   // ---- stage the key matrices with TMA bulk copies (one mbarrier, one phase) ----
@@ -181,8 +185,8 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     if (RES & RES_L) total += mat_bytes;
     if (RES & RES_P) total += (uint32_t)n * D * 4;
     mbar_expect_tx(bar, total);
-    if (RES & RES_V) bulk_g2s(sV, gkeys + (size_t)n * KS, mat_bytes, bar);
-    if (RES & RES_L) bulk_g2s(sL, gkeys + (size_t)2 * n * KS, mat_bytes, bar);
+    if (RES & RES_V) bulk_g2s(sV, gV, mat_bytes, bar);
+    if (RES & RES_L) bulk_g2s(sL, gL, mat_bytes, bar);
     if (RES & RES_P) bulk_g2s(sP, gpsc, (uint32_t)n * D * 4, bar);
   }
   // K' -> registers: the 16 features of head `warp` for nodes lane + 32 p (one-time global read)
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < n) v = __ldg(reinterpret_cast<const float4*>(gkeys + (size_t)j * KS) + swz(warp * 4 + i, j));
+      if (j < n) v = __ldg(reinterpret_cast<const float4*>(gK + (size_t)j * KS) + warp * 4 + i);
       kreg[p][4 * i] = v.x; kreg[p][4 * i + 1] = v.y; kreg[p][4 * i + 2] = v.z; kreg[p][4 * i + 3] = v.w;
     }
   }
@@ -216,9 +220,30 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   }
   __syncthreads();
   mbar_wait(bar, 0);
+  // the staged rows are plain: permute the 16-byte chunks of every aligned 8-chunk group by (node & 7) in place (swz()
+  // below), so that lanes reading the same logical chunk of 8 consecutive nodes hit 8 different bank groups
+  {
+    auto swizzle_rows = [&](float* m) {
+      for (int it = tid; it < n * 4; it += 256) {
+        const int j = it >> 2, x = j & 7;
+        if (x == 0) continue;
+        float4* grp = reinterpret_cast<float4*>(m + (size_t)j * KS) + (it & 3) * 8;
+        const int rot = lane & 7;                 // lanes start at different chunks: no bank conflicts in this pass either
+        float4 tmp[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) tmp[c] = grp[(c + rot) & 7];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) grp[((c + rot) & 7) ^ x] = tmp[c];
+      }
+    };
+    if (RES & RES_V) swizzle_rows(sV);
+    if (RES & RES_L) swizzle_rows(sL);
+    __syncthreads();
+  }
 
-  const float* Vm = (RES & RES_V) ? sV : gkeys + (size_t)n * KS;
-  const float* Lm = (RES & RES_L) ? sL : gkeys + (size_t)2 * n * KS;
+  const float* Vm = (RES & RES_V) ? sV : gV;
+  const float* Lm = (RES & RES_L) ? sL : gL;
+  constexpr bool SWV = (RES & RES_V) != 0, SWL = (RES & RES_L) != 0;     // global rows are read as they are
   const float* Pm = (RES & RES_P) ? sP : gpsc;
 
   // ---- constants of the node(s) whose feasibility this thread evaluates (node = tid + 256 k) ----
@@ -397,7 +422,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
           const float4* vr = reinterpret_cast<const float4*>(Vm + (size_t)j * KS);
   #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 v = vr[swz(h * 4 + i, j)];
+            const float4 v = vr[SWV ? swz(h * 4 + i, j) : h * 4 + i];
             acc[4 * i + 0] = fmaf(ev, v.x, acc[4 * i + 0]);
             acc[4 * i + 1] = fmaf(ev, v.y, acc[4 * i + 1]);
             acc[4 * i + 2] = fmaf(ev, v.z, acc[4 * i + 2]);
@@ -413,7 +438,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
           const float4* vr = reinterpret_cast<const float4*>(Vm + (size_t)j * KS);
   #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 v = vr[swz(h * 4 + i, j)];
+            const float4 v = vr[SWV ? swz(h * 4 + i, j) : h * 4 + i];
             acc[4 * i + 0] = fmaf(e[p], v.x, acc[4 * i + 0]);
             acc[4 * i + 1] = fmaf(e[p], v.y, acc[4 * i + 1]);
             acc[4 * i + 2] = fmaf(e[p], v.z, acc[4 * i + 2]);
@@ -466,7 +491,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         if (valid) {
           const float4* lr = reinterpret_cast<const float4*>(Lm + (size_t)j * KS);
           const float4* o4 = reinterpret_cast<const float4*>(s_o);
-          const int sw = (fg ^ j) & 7;
+          const int sw = SWL ? ((fg ^ j) & 7) : fg;
           const float u0 = dot4(o4[fg], lr[sw], 0.f), u1 = dot4(o4[8 + fg], lr[8 + sw], 0.f);
           const float u2 = dot4(o4[16 + fg], lr[16 + sw], 0.f), u3 = dot4(o4[24 + fg], lr[24 + sw], 0.f);
           u = (u0 + u1) + (u2 + u3);
@@ -526,10 +551,10 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
           float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
   #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            u0 = dot4(o4[i], lr[swz(half * 16 + i, j)], u0);
-            u1 = dot4(o4[i + 1], lr[swz(half * 16 + i + 1, j)], u1);
-            u2 = dot4(o4[i + 2], lr[swz(half * 16 + i + 2, j)], u2);
-            u3 = dot4(o4[i + 3], lr[swz(half * 16 + i + 3, j)], u3);
+            u0 = dot4(o4[i], lr[SWL ? swz(half * 16 + i, j) : half * 16 + i], u0);
+            u1 = dot4(o4[i + 1], lr[SWL ? swz(half * 16 + i + 1, j) : half * 16 + i + 1], u1);
+            u2 = dot4(o4[i + 2], lr[SWL ? swz(half * 16 + i + 2, j) : half * 16 + i + 2], u2);
+            u3 = dot4(o4[i + 3], lr[SWL ? swz(half * 16 + i + 3, j) : half * 16 + i + 3], u3);
           }
           u = (u0 + u1) + (u2 + u3);
         }

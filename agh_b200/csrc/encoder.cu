@@ -8,7 +8,7 @@
 //
 // CUDA-core back end (agh_set_gemm_backend(0) / AGH_GEMM=simt): all dense contractions go through one tiled SGEMM
 // (128x128x16 tiles, 8x8 register micro-tile, register double buffering) whose epilogue fuses bias / ReLU /
-// residual + BatchNorm scale-shift / the scatter into the swizzled key layout the decode kernel stages with TMA;
+// residual + BatchNorm scale-shift / the four [M][128] outputs of the decoder projection (K', V, LK', P_sc);
 // self-attention is a flash-style kernel: two heads per CTA, K_h/V_h staged in shared memory, two query rows per
 // thread with a base-2 online softmax, so no [n,n] score matrix ever reaches HBM.  The default back end replaces
 // both with tensor-core kernels behind the same launch sequence.
@@ -143,15 +143,9 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
         v.x = fmaf(r.x + v.x, s.x, t.x); v.y = fmaf(r.y + v.y, s.y, t.y);
         v.z = fmaf(r.z + v.z, s.z, t.z); v.w = fmaf(r.w + v.w, s.w, t.w);
       }
-      if (EPI == EPI_DEC) {
-        if (col < 3 * D) {
-          const int mat = col / D, c = col % D;
-          const int bi = row / g.n, j = row % g.n;
-          const int c4 = c >> 2, pc4 = (c4 & ~7) | ((c4 ^ j) & 7);       // chunk swizzle, see decode.cu swz()
-          *reinterpret_cast<float4*>(g.keys + (((size_t)bi * 3 + mat) * g.n + j) * KS + pc4 * 4) = v;
-        } else {
-          *reinterpret_cast<float4*>(g.psc + (size_t)row * D + (col - 3 * D)) = v;
-        }
+      if (EPI == EPI_DEC) {       // four plain [M][128] matrices: K', V, LK' (keys[0..2]) and P_sc
+        float* base = col < 3 * D ? g.keys + (size_t)(col / D) * g.M * D : g.psc;
+        *reinterpret_cast<float4*>(base + (size_t)row * D + col % D) = v;
       } else {
         *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + col) = v;
       }

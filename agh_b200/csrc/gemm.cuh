@@ -15,7 +15,7 @@ struct GemmArgs {
   const float* bias;       // [Nc] or null
   const float* res; int ldr;   // residual
   const float* bn_s; const float* bn_t;
-  // EPI_DEC: scatter into the decode kernel's key layout
+  // EPI_DEC: Nc = 512 = four [M][128] outputs: keys[0] = K', keys[1] = V, keys[2] = LK' (keys is [3][M][128]), psc
   float* keys; float* psc; int n;
 };
 

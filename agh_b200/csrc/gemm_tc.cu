@@ -157,10 +157,11 @@ struct Cfg {
 // 16-byte accesses: bit EPI of the mask.  Overridable at compile time for A/B measurements
 // (AGH_NVCC_EXTRA=-DAGH_TC_TRANSPOSE_MASK=..).  Measured per launch at M = 1.01 M rows with the eight epilogue
 // warps (transposed vs row-wise): QKV/plain 612 vs ~1000 us, out-proj 508 vs ~630, FF2 1010 vs ~1250 (residual+BN
-// with the residual prefetched), FF1/bias+ReLU 820 vs 1200, key scatter 1690 vs 1250 -> everything but the
-// swizzled key scatter is transposed.  (With four epilogue warps the shuffles made FF1 slower transposed.)
+// with the residual prefetched), FF1/bias+ReLU 820 vs 1200 -> every epilogue is transposed (the decoder projection
+// writes four plain [M][128] matrices; its former swizzled 16-byte scatter was 1250 us row-wise, 1690 transposed).
+// (With four epilogue warps the shuffles made FF1 slower transposed.)
 #ifndef AGH_TC_TRANSPOSE_MASK
-#define AGH_TC_TRANSPOSE_MASK 0x7
+#define AGH_TC_TRANSPOSE_MASK 0xf
 #endif
 __host__ __device__ constexpr bool epi_transposed(int epi) { return (AGH_TC_TRANSPOSE_MASK >> epi) & 1; }
 
@@ -305,6 +306,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // four 32-column chunks of the tile between them =================
     const int q = warp & 3;
     const int chalf = (warp - 6) >> 2;                          // 0: chunks 0,1   1: chunks 2,3
+    // EPI_DEC: the four 128-column slabs are four plain [M][128] matrices -- K', V, LK' (keys[0..2]) and P_sc -- so the
+    // epilogue is the plain one with a per-slab base (shifted by n0 because `col` below is the GEMM's global column)
+    float* Cb = g.C;
+    int ldc = g.ldc;
+    if (EPI == EPI_DEC) {
+      Cb = (blockIdx.y < 3 ? g.keys + (size_t)blockIdx.y * g.M * D : g.psc) - n0;
+      ldc = D;
+    }
     constexpr int CH_PER_WARP = (BN / 32) / (EPI_WARPS / 4);
     uint32_t tile = 0;
     for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++tile) {
@@ -352,8 +361,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // row-wise epilogue: this thread owns row `row0 + lane`, 8 x 16-byte accesses per 32-column chunk
           const int row = row0 + lane;
           if (row >= g.M) continue;
-          int bi = 0, j = 0;
-          if (EPI == EPI_DEC) { bi = row / g.n; j = row % g.n; }
 #pragma unroll
           for (int v4 = 0; v4 < 8; ++v4) {
             const int col = n0 + c0 + v4 * 4;
@@ -372,17 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v.x = fmaf(rr.x + v.x, sc.x, sh.x); v.y = fmaf(rr.y + v.y, sc.y, sh.y);
               v.z = fmaf(rr.z + v.z, sc.z, sh.z); v.w = fmaf(rr.w + v.w, sc.w, sh.w);
             }
-            if (EPI == EPI_DEC) {
-              if (col < 3 * D) {
-                const int mat = col / D, c = col % D;
-                const int c4 = c >> 2, pc4 = (c4 & ~7) | ((c4 ^ j) & 7);       // chunk swizzle, see decode.cu swz()
-                *reinterpret_cast<float4*>(g.keys + (((size_t)bi * 3 + mat) * g.n + j) * KS + pc4 * 4) = v;
-              } else {
-                *reinterpret_cast<float4*>(g.psc + (size_t)row * D + (col - 3 * D)) = v;
-              }
-            } else {
-              *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + col) = v;
-            }
+            *reinterpret_cast<float4*>(Cb + (size_t)row * ldc + col) = v;
           }
           continue;
         }
@@ -404,8 +401,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float bias = 0.f, sc = 1.f, sh = 0.f;
         if (EPI == EPI_BIAS_RELU || (EPI == EPI_RES_BN && g.bias != nullptr)) bias = s_vec[c0 + lane];
         if (EPI == EPI_RES_BN) { sc = s_vec[BN + c0 + lane]; sh = s_vec[2 * BN + c0 + lane]; }
-        int mat = 0, cc = 0, bi = 0, j = 0;
-        if (EPI == EPI_DEC) { mat = col / D; cc = col % D; bi = row0 / g.n; j = row0 % g.n; }
         if (EPI == EPI_RES_BN) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = fmaf(rr[i] + (r[i] + bias), sc, sh);
@@ -416,19 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int row = row0 + i;
           float v = r[i];
           if (EPI == EPI_BIAS_RELU) v = fmaxf(v + bias, 0.f);
-          if (row < g.M) {
-            if (EPI == EPI_DEC) {
-              if (mat < 3) {
-                const int c4 = cc >> 2, pc4 = (c4 & ~7) | ((c4 ^ j) & 7);       // chunk swizzle, see decode.cu swz()
-                g.keys[(((size_t)bi * 3 + mat) * g.n + j) * KS + pc4 * 4 + (cc & 3)] = v;
-              } else {
-                g.psc[(size_t)row * D + cc] = v;
-              }
-            } else {
-              g.C[(size_t)row * g.ldc + col] = v;
-            }
-          }
-          if (EPI == EPI_DEC) { if (++j == g.n) { j = 0; ++bi; } }
+          if (row < g.M) Cb[(size_t)row * ldc + col] = v;
         }
       }
     }

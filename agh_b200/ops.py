@@ -128,10 +128,10 @@ def encode_layers(wblob, h0) -> torch.Tensor:
 
 
 def precompute(wblob, h, task: FleetTask):
-    """a4: keys [B,3,n,128], psc [B,n,128], qbase [B,128]."""
+    """a4: keys [3,B,n,128] (K', V, LK' as plain row-major matrices), psc [B,n,128], qbase [B,128]."""
     B, n, _ = h.shape
     dev = h.device
-    keys = torch.empty(B, 3, n, KS, dtype=torch.float32, device=dev)
+    keys = torch.empty(3, B, n, KS, dtype=torch.float32, device=dev)
     psc = torch.empty(B, n, D, dtype=torch.float32, device=dev)
     qbase = torch.empty(B, D, dtype=torch.float32, device=dev)
     check(lib().agh_precompute(ptr(wblob, torch.float32), ptr(h, torch.float32),

@@ -97,7 +97,7 @@ int agh_init_embed(const float* wblob, const uint8_t* coord, const float* demand
 int agh_encode_layers(const float* wblob, const float* h0, int B, int N, float* h_out, void* workspace, void* stream);
 
 /* ---- a4: decoder precompute (attention_model.py:392-414,604-611) ---------------------------
- *   h[B][n][128] -> keys[B][3][n][128] (K'/4, V, LK'), psc[B][n][128], qbase[B][128]
+ *   h[B][n][128] -> keys[3][B][n][128] (K', V, LK': three plain row-major matrices), psc[B][n][128], qbase[B][128]
  *   fleet_ids[B] i32 (0..9) or NULL with `fleet` used for every instance.
  */
 int agh_precompute(const float* wblob, const float* h, const int32_t* fleet_ids, int fleet, int B, int N,
@@ -107,7 +107,7 @@ int agh_precompute(const float* wblob, const float* h, const int32_t* fleet_ids,
  *      state_agh.py:60-174), one CTA per instance for all T steps ----------------------------- */
 typedef struct {
   /* inputs */
-  const float* keys;       /* [B][3][n][128] */
+  const float* keys;       /* [3][KB][n][128], KB = key_mod if key_mod > 0 else B */
   const float* psc;        /* [B][n][128] */
   const float* qbase;      /* [B][128] */
   const uint8_t* coord;    /* [B][n] */
