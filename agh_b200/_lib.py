@@ -38,12 +38,26 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     extra = os.environ.get('AGH_NVCC_EXTRA', '').split()          # e.g. -DAGH_TC_TRANSPOSE_MASK=0x7 for A/B builds
-    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    flags = [f for f in NVCC_FLAGS if f != '-shared'] + extra + (['-Xptxas', '-v'] if verbose else [])
+    objdir = os.path.join(CSRC, '_obj')
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):                                          # one translation unit per process, in parallel
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+        return obj, subprocess.run([nvcc] + flags + ['-c', src, '-o', obj], capture_output=True, text=True)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(len(srcs)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    for obj, res in results:
+        if res.returncode != 0:
+            raise AghError('nvcc failed:\n' + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    res = subprocess.run([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB_PATH] + [o for o, _ in results],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise AghError('nvcc failed:\n' + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise AghError('nvcc link failed:\n' + res.stdout + res.stderr)
     return LIB_PATH
 
 
