@@ -119,6 +119,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));      // the caller issues tcgen05.wait::ld before reading r[]
 }
 
+// 16 TMEM lanes x 32 columns in the mma "C fragment" distribution: thread (g = lane / 4, t = lane % 4) receives, for
+// every 8-column group k, r[4k], r[4k+1] = (lane base + g, columns 8k + 2t, 8k + 2t + 1) and r[4k+2], r[4k+3] = the
+// same columns of lane base + g + 8.  A quad therefore holds 32 contiguous bytes of one row: global accesses made
+// straight from this layout are whole 32-byte sectors, with no transpose.
+__device__ __forceinline__ void tmem_ld16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));      // the caller issues tcgen05.wait::ld before reading r[]
+}
+
 // x = hi + lo with hi = rn_tf32(x) and lo = rn_tf32(x - hi): both exactly representable in tf32 (so it does not
 // matter whether the tensor core truncates or rounds its fp32 containers) and the rounding errors are unbiased.
 // Round-to-nearest (ties away) with an integer add + mask: cvt.rna.tf32.f32 runs on the slow conversion pipe.
@@ -164,6 +177,16 @@ struct Cfg {
 #define AGH_TC_TRANSPOSE_MASK 0xf
 #endif
 __host__ __device__ constexpr bool epi_transposed(int epi) { return (AGH_TC_TRANSPOSE_MASK >> epi) & 1; }
+// Bit EPI set: read the accumulators in the 16x256b fragment distribution and access global memory straight from it
+// (whole 32-byte sectors, no shuffles) instead of the 32x32b row distribution with the epilogues above.  Measured per
+// launch at M = 1.01 M rows (fragment vs transposed): out-proj 292 vs 503 us, FF2 968 vs 998 (residual + BN: the
+// residual is read in the same distribution and the 32x32 transposes go away); QKV 683 vs 608, FF1 842 vs 812, decoder
+// projection 860 vs 830 (store-heavy shapes: four times as many 32-byte store requests as 128-byte rows) -> only the
+// residual epilogue uses it.
+#ifndef AGH_TC_FRAG_MASK
+#define AGH_TC_FRAG_MASK 0x4
+#endif
+__host__ __device__ constexpr bool epi_frag(int epi) { return (AGH_TC_FRAG_MASK >> epi) & 1; }
 
 template <int EPI, bool WRES>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -328,10 +351,81 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) dst[i] = (row0 + i < g.M) ? __ldg(src + (size_t)i * g.ldr) : 0.f;
       };
-      if (EPI == EPI_RES_BN && epi_transposed(EPI)) load_res(c_first, rr);
+      // fragment domain: thread (g8, t4) owns rows row0 + 8 rq + g8 (rq = 0..3) and column pairs 8 k + 2 t4 (k = 0..3)
+      const int g8 = lane >> 2, t4 = lane & 3;
+      float2 fres[16];                                            // residual, index rq * 4 + k
+      auto load_res_frag = [&](int c0) {
+#pragma unroll
+        for (int rq = 0; rq < 4; ++rq) {
+          const int row = row0 + rq * 8 + g8;
+          const float* src = g.res + (size_t)row * g.ldr + n0 + c0 + 2 * t4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            fres[rq * 4 + k] = row < g.M ? __ldg(reinterpret_cast<const float2*>(src + 8 * k)) : make_float2(0.f, 0.f);
+        }
+      };
+      if (EPI == EPI_RES_BN) {
+        if (epi_frag(EPI)) load_res_frag(c_first);
+        else if (epi_transposed(EPI)) load_res(c_first, rr);
+      }
       mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t t_acc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
+      if (epi_frag(EPI)) {
+#pragma unroll 1
+        for (int c0 = c_first; c0 <= c_last; c0 += 32) {
+          float r[32];                                            // index (rq / 2) * 16 + k * 4 + (rq % 2) * 2 + {0, 1}
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {                        // TMEM lanes [0,16) and [16,32) of the quarter
+            uint32_t ra[16];
+            const uint32_t ta = t_acc + ((uint32_t)(hh * 16) << 16) + (uint32_t)c0;
+            tmem_ld16x256b_x4(ta, ra);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[hh * 16 + i] = __uint_as_float(ra[i]);
+#pragma unroll
+            for (int a = 1; a <= C::NACC; ++a) {                   // further hi.hi partials, then the cross terms
+              tmem_ld16x256b_x4(ta + (uint32_t)(a * BN), ra);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[hh * 16 + i] += __uint_as_float(ra[i]);
+            }
+          }
+          if (c0 == c_last) {             // all of this warp's columns of the accumulator set are in registers: hand it back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(ab));
+          }
+#ifdef AGH_TC_SKIP_EPILOGUE
+          if (r[0] != 12345.678f) continue;
+#endif
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int cl = c0 + 8 * k + 2 * t4;                   // column within the CTA's 128-column slab
+            float2 bias = make_float2(0.f, 0.f), sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+            if (EPI == EPI_BIAS_RELU || (EPI == EPI_RES_BN && g.bias != nullptr)) bias = *reinterpret_cast<const float2*>(s_vec + cl);
+            if (EPI == EPI_RES_BN) {
+              sc = *reinterpret_cast<const float2*>(s_vec + BN + cl);
+              sh = *reinterpret_cast<const float2*>(s_vec + 2 * BN + cl);
+            }
+#pragma unroll
+            for (int rq = 0; rq < 4; ++rq) {
+              const int row = row0 + rq * 8 + g8;
+              const int ri = (rq >> 1) * 16 + k * 4 + (rq & 1) * 2;
+              float2 v = make_float2(r[ri], r[ri + 1]);
+              if (EPI == EPI_BIAS_RELU) {
+                v.x = fmaxf(v.x + bias.x, 0.f); v.y = fmaxf(v.y + bias.y, 0.f);
+              } else if (EPI == EPI_RES_BN) {
+                const float2 rs = fres[rq * 4 + k];
+                v.x = fmaf(rs.x + (v.x + bias.x), sc.x, sh.x); v.y = fmaf(rs.y + (v.y + bias.y), sc.y, sh.y);
+              }
+              if (row < g.M) *reinterpret_cast<float2*>(Cb + (size_t)row * ldc + n0 + cl) = v;
+            }
+          }
+          if (EPI == EPI_RES_BN && c0 < c_last) load_res_frag(c0 + 32);      // next chunk's residual: in flight during its TMEM reads
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = c_first; c0 <= c_last; c0 += 32) {
         float r[32];
