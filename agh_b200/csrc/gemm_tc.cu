@@ -160,7 +160,10 @@ struct Cfg {
   static constexpr int STAGE_BYTES = WRES ? 2 * BLK : 4 * BLK;
   static constexpr int WRES_BYTES = WRES ? 8 * BLK : 0;
   static constexpr int NACC = WRES ? 1 : 3;
-  static constexpr int NBUF = WRES ? 2 : 1;
+#ifndef AGH_TC_NBUF
+#define AGH_TC_NBUF 2
+#endif
+  static constexpr int NBUF = WRES ? AGH_TC_NBUF : 1;
   static constexpr int NBARS = 3 * STAGES + 2 * NBUF + 2;
   static constexpr int VEC_OFF = (8 * NBARS + 16 + 15) & ~15;      // per-column epilogue vectors: bias, bn scale, bn shift
   static constexpr int SMEM = WRES_BYTES + STAGES * STAGE_BYTES + 1024 /*align*/ + VEC_OFF + 3 * BN * 4;
@@ -183,6 +186,18 @@ __host__ __device__ constexpr bool epi_transposed(int epi) { return (AGH_TC_TRAN
 // residual is read in the same distribution and the 32x32 transposes go away); QKV 683 vs 608, FF1 842 vs 812, decoder
 // projection 860 vs 830 (store-heavy shapes: four times as many 32-byte store requests as 128-byte rows) -> only the
 // residual epilogue uses it.
+// Bit EPI set: the MMA computes the TRANSPOSED tile, D[c][r] = sum_k W[c][k] A[r][k]: the weight slab is the "A" operand
+// (its 128 rows = output columns -> TMEM lanes) and the activation tile the "B" operand (its 128 rows -> TMEM columns).
+// Both are K-major SWIZZLE_128B blocks, so this is only an exchange of the two shared-memory descriptors -- but a
+// 32x32b TMEM load then hands every thread ONE output column and 32 consecutive rows, i.e. the register layout the
+// in-register transpose used to build with 80 shuffles + 160 selects per chunk: every store (and residual load) of a
+// warp is one coalesced 128-byte row segment for free.  Measured per launch at M = 1.01 M rows (swapped vs the best of
+// the other epilogues): decoder projection 736 vs 830 us, but QKV 646 vs 608, FF1 923 vs 812, out-proj 377 vs 292,
+// FF2 1024 vs 968 -- the shuffles were not what bounds those shapes -- so only the decoder projection uses it.
+#ifndef AGH_TC_SWAP_MASK
+#define AGH_TC_SWAP_MASK 0x8
+#endif
+__host__ __device__ constexpr bool epi_swap(int epi) { return (AGH_TC_SWAP_MASK >> epi) & 1; }
 #ifndef AGH_TC_FRAG_MASK
 #define AGH_TC_FRAG_MASK 0x4
 #endif
@@ -293,9 +308,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ks = kb * (BK / 8) + k;
             const uint32_t t_cross = t_acc + C::NACC * BN;
             const uint32_t t_main = t_acc + (ks % C::NACC) * BN;
-            umma_tf32(t_cross, da_lo + adv, dw_hi + adv, idesc, ks != 0);
-            umma_tf32(t_cross, da_hi + adv, dw_lo + adv, idesc, 1);
-            umma_tf32(t_main, da_hi + adv, dw_hi + adv, idesc, ks >= C::NACC);
+            if (epi_swap(EPI)) {   // D^T: weights are the M-side operand
+              umma_tf32(t_cross, dw_hi + adv, da_lo + adv, idesc, ks != 0);
+              umma_tf32(t_cross, dw_lo + adv, da_hi + adv, idesc, 1);
+              umma_tf32(t_main, dw_hi + adv, da_hi + adv, idesc, ks >= C::NACC);
+            } else {
+              umma_tf32(t_cross, da_lo + adv, dw_hi + adv, idesc, ks != 0);
+              umma_tf32(t_cross, da_hi + adv, dw_lo + adv, idesc, 1);
+              umma_tf32(t_main, da_hi + adv, dw_hi + adv, idesc, ks >= C::NACC);
+            }
           }
           umma_commit(bar_empty(s));                             // frees the stage when these MMAs retire
           if (kb == nkb - 1) umma_commit(bar_tfull(ab));         // accumulator set complete
@@ -341,6 +362,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t tile = 0;
     for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++tile) {
       const int ab = tile % C::NBUF;
+      if (epi_swap(EPI)) {
+        // thread = one output column (TMEM lane), chunks of 32 consecutive rows (TMEM columns); the two warps of a lane
+        // quarter split the tile's four row chunks between them
+        const int cl = q * 32 + lane, col = n0 + cl;
+        const int r_first = chalf * CH_PER_WARP * 32, r_last = r_first + (CH_PER_WARP - 1) * 32;
+        float bias = 0.f, sc = 1.f, sh = 0.f;
+        if (EPI == EPI_BIAS_RELU || (EPI == EPI_RES_BN && g.bias != nullptr)) bias = s_vec[cl];
+        if (EPI == EPI_RES_BN) { sc = s_vec[BN + cl]; sh = s_vec[2 * BN + cl]; }
+        float rs[32];                                           // residual of rows mt*BM + rc + i, this thread's column
+        auto load_res_sw = [&](int rc) {
+          const int rbase = mt * BM + rc;
+          const float* src = g.res + (size_t)rbase * g.ldr + col;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rs[i] = (rbase + i < g.M) ? __ldg(src + (size_t)i * g.ldr) : 0.f;
+        };
+        if (EPI == EPI_RES_BN) load_res_sw(r_first);            // independent of the MMAs: issued before the accumulator is ready
+        mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t t_acc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int rc = r_first; rc <= r_last; rc += 32) {
+          float r[32];
+          {   // accumulators one after the other (hi.hi partials, then the cross terms), added in fp32 round-to-nearest
+            uint32_t ra[32];
+            tmem_ld32(t_acc + (uint32_t)rc, ra);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(ra[i]);
+#pragma unroll
+            for (int a = 1; a <= C::NACC; ++a) {
+              tmem_ld32(t_acc + (uint32_t)(a * BN + rc), ra);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] += __uint_as_float(ra[i]);
+            }
+          }
+          if (rc == r_last) {             // all of this warp's share of the accumulator set is in registers: hand it back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(ab));
+          }
+#ifdef AGH_TC_SKIP_EPILOGUE
+          if (r[0] != 12345.678f) continue;
+#endif
+          if (EPI == EPI_RES_BN) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = fmaf(rs[i] + (r[i] + bias), sc, sh);
+            if (rc < r_last) load_res_sw(rc + 32);              // next chunk's residual flies while this chunk is stored
+          }
+          const int rbase = mt * BM + rc;
+          float* dst = Cb + (size_t)rbase * ldc + col;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = r[i];
+            if (EPI == EPI_BIAS_RELU) v = fmaxf(v + bias, 0.f);
+            if (rbase + i < g.M) dst[(size_t)i * ldc] = v;
+          }
+        }
+        continue;
+      }
       const int row0 = mt * BM + q * 32;
       const int c_first = chalf * CH_PER_WARP * 32, c_last = c_first + (CH_PER_WARP - 1) * 32;
       // transposed domain: lane = column, rr[i] = residual of row row0 + i.  The residual does not depend on the
