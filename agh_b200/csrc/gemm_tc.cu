@@ -203,6 +203,22 @@ __host__ __device__ constexpr bool epi_swap(int epi) { return (AGH_TC_SWAP_MASK 
 #endif
 __host__ __device__ constexpr bool epi_frag(int epi) { return (AGH_TC_FRAG_MASK >> epi) & 1; }
 
+// -DAGH_TC_TRACE: CTA (0,0) of the first large launches stamps %globaltimer at every pipeline hand-off and prints the
+// per-role timeline at the end (tools/gemm_timeline.py turns it into per-stage durations).  Off in the product build.
+#ifdef AGH_TC_TRACE
+constexpr int TR_CAP = 96;
+__device__ unsigned long long g_trace[8][TR_CAP];
+__device__ int g_trace_launches = 0;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TR(role, idx) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (int)(idx) < TR_CAP) g_trace[role][idx] = gtime(); } while (0)
+#else
+#define TR(role, idx) do { } while (0)
+#endif
+
 template <int EPI, bool WRES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
@@ -273,6 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_empty(s), ((it / STAGES) & 1) ^ 1);
+          TR(0, it);
           unsigned char* st = ring + s * C::STAGE_BYTES;
           mbar_expect_tx(bar_raw(s), WRES ? BLK : 2 * BLK);
           tma_load_2d(smem_u32(st), &tmA, bar_raw(s), kb * BK, mt * BM);
@@ -298,6 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(bar_split(s), (it / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
+          TR(3, it);
           const uint32_t st = smem_u32(ring + s * C::STAGE_BYTES);
           const uint64_t da_hi = umma_desc(st), da_lo = umma_desc(st + BLK);
           const uint32_t wb = WRES ? smem_u32(wres + kb * BLK) : st + 2 * BLK;
@@ -319,6 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           umma_commit(bar_empty(s));                             // frees the stage when these MMAs retire
+          TR(4, it);
           if (kb == nkb - 1) umma_commit(bar_tfull(ab));         // accumulator set complete
         }
         __syncwarp();
@@ -338,11 +357,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait(bar_raw(s), (it / STAGES) & 1);
+        if (t == 0) TR(1, it);
         unsigned char* st = ring + s * C::STAGE_BYTES;
         split_block(st, st + BLK, BLK / 16, t);
         if (!WRES) split_block(st + 2 * BLK, st + 3 * BLK, BLK / 16, t);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(bar_split(s));
+        if (t == 0) TR(2, it);
       }
     }
   } else {
@@ -379,6 +400,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         if (EPI == EPI_RES_BN) load_res_sw(r_first);            // independent of the MMAs: issued before the accumulator is ready
         mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
+      if (warp == 6 && lane == 0) TR(5, tile);
+        if (warp == 6 && lane == 0) TR(5, tile);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t_acc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -402,6 +425,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty(ab));
+          if (warp == 6 && lane == 0) TR(6, tile);
+            if (warp == 6 && lane == 0) TR(6, tile);
           }
 #ifdef AGH_TC_SKIP_EPILOGUE
           if (r[0] != 12345.678f) continue;
@@ -420,6 +445,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (rbase + i < g.M) dst[(size_t)i * ldc] = v;
           }
         }
+        if (warp == 6 && lane == 0) TR(7, tile);
         continue;
       }
       const int row0 = mt * BM + q * 32;
@@ -450,6 +476,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else if (epi_transposed(EPI)) load_res(c_first, rr);
       }
       mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
+      if (warp == 6 && lane == 0) TR(5, tile);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t t_acc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
       if (epi_frag(EPI)) {
@@ -476,6 +503,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty(ab));
+          if (warp == 6 && lane == 0) TR(6, tile);
+            if (warp == 6 && lane == 0) TR(6, tile);
           }
 #ifdef AGH_TC_SKIP_EPILOGUE
           if (r[0] != 12345.678f) continue;
@@ -505,6 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (EPI == EPI_RES_BN && c0 < c_last) load_res_frag(c0 + 32);      // next chunk's residual: in flight during its TMEM reads
         }
+        if (warp == 6 && lane == 0) TR(7, tile);
         continue;
       }
 #pragma unroll 1
@@ -528,6 +558,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty(ab));
+          if (warp == 6 && lane == 0) TR(6, tile);
         }
 #ifdef AGH_TC_SKIP_EPILOGUE      // measurement only: main-loop-bound time (results are NOT written)
         if (r[0] != 12345.678f) continue;
@@ -589,11 +620,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (row < g.M) Cb[(size_t)row * ldc + col] = v;
         }
       }
+      if (warp == 6 && lane == 0) TR(7, tile);
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+#ifdef AGH_TC_TRACE
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g.M > 500000) {
+    const int l = atomicAdd(&g_trace_launches, 1);
+    if (l < 10) {
+      const int tiles = (num_mt + (int)gridDim.x - 1) / (int)gridDim.x;
+      const unsigned long long base = g_trace[0][0];
+      for (int role = 0; role < 8; ++role) {
+        const int cnt = role < 5 ? tiles * nkb : tiles;
+        for (int i = 0; i < cnt && i < TR_CAP; ++i)
+          printf("TRACE %d %d %d %d %d %lld\n", l, EPI, (int)WRES, role, i, (long long)(g_trace[role][i] - base));
+      }
+    }
+  }
+#endif
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
