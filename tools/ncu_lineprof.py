@@ -1,6 +1,14 @@
+"""Per-source-line profile of one kernel from an ncu report.
+
+    cuobjdump -xelf all agh_b200/libagh_b200.so && nvdisasm -g -c decode.sm_100a.cubin > lines.txt
+    ncu -i report.ncu-rep --page source --csv > src.csv
+    python tools/ncu_lineprof.py <mangled kernel name> src.csv agh_b200/csrc/decode.cu lines.txt
+
+Joins the SASS addresses of the report with nvdisasm's line table and prints, per source line, the share of stall
+samples and of executed instructions."""
 import re, csv, collections, sys
 fn=sys.argv[1]; sass_csv=sys.argv[2]; srcfile=sys.argv[3]
-txt=open('/tmp/dec_all_lines.txt').read().split('\n')
+txt=open(sys.argv[4] if len(sys.argv) > 4 else '/tmp/dec_all_lines.txt').read().split('\n')
 start=None
 for i,l in enumerate(txt):
     if l.startswith('.text.'+fn+':'): start=i; break
