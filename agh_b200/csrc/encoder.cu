@@ -340,13 +340,19 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
     const float* lw = wblob + W_LAYER0 + (size_t)l * L_SIZE;
     const float* tw = wblob + W_TC0 + (size_t)l * T_SIZE;
     float* xout = (l == LAYERS - 1) ? h_out : xa;
+    // Between two tensor-core kernels the wide intermediates (qkv, FF hidden) are kept SLAB-MAJOR -- Nc/128 separate
+    // [M][128] matrices -- so that every CTA of the producing GEMM stores one contiguous 64 KB block per tile
+    // (measured: the same K = 128 x Nc = 512 GEMM takes 570 us with that output form and 815 us row-major).
+    static const bool mha_simt = getenv("AGH_MHA") != nullptr && strcmp(getenv("AGH_MHA"), "simt") == 0;
+    const bool tcg = use_tensor_cores();
+    const bool qkv_slab = tcg && !mha_simt;
     GemmArgs g{};
     g.A = x; g.lda = D; g.W = lw + L_WQKV; g.Wt = tw + T_WQKV; g.C = qkv; g.ldc = 3 * D; g.M = M; g.K = D; g.Nc = 3 * D;
+    g.c_slab = qkv_slab;
     int rc = launch_gemm<EPI_PLAIN>(g, st);
     if (rc) return rc;
-    static const bool mha_simt = getenv("AGH_MHA") != nullptr && strcmp(getenv("AGH_MHA"), "simt") == 0;
-    if (use_tensor_cores() && !mha_simt) {
-      rc = launch_mha_mma(qkv, B, n, heads, st);
+    if (tcg && !mha_simt) {
+      rc = launch_mha_mma(qkv, qkv_slab, B, n, heads, st);
       if (rc) return rc;
     } else {
       mha_kernel<<<B * (H / 2), mha_threads, mha_smem, st>>>(qkv, n, heads);
@@ -359,11 +365,13 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
     if (rc) return rc;
     g = GemmArgs{};
     g.A = x1; g.lda = D; g.W = lw + L_W1T; g.Wt = tw + T_W1; g.C = hid; g.ldc = FF; g.M = M; g.K = D; g.Nc = FF; g.bias = lw + L_B1;
+    g.c_slab = tcg;
     rc = launch_gemm<EPI_BIAS_RELU>(g, st);
     if (rc) return rc;
     g = GemmArgs{};
     g.A = hid; g.lda = FF; g.W = lw + L_W2T; g.Wt = tw + T_W2; g.C = xout; g.ldc = D; g.M = M; g.K = FF; g.Nc = D; g.bias = lw + L_B2;
     g.res = x1; g.ldr = D; g.bn_s = lw + L_BN2S; g.bn_t = lw + L_BN2T;
+    g.a_slab = tcg;
     rc = launch_gemm<EPI_RES_BN>(g, st);
     if (rc) return rc;
     x = xout;

@@ -17,12 +17,15 @@ struct GemmArgs {
   const float* bn_s; const float* bn_t;
   // EPI_DEC: Nc = 512 = four [M][128] outputs: keys[0] = K', keys[1] = V, keys[2] = LK' (keys is [3][M][128]), psc
   float* keys; float* psc; int n;
+  // tensor-core path only: C written / A read as Nc/128 (K/128) separate [M][128] matrices ("slab-major": every CTA's
+  // 128 x 128 output tile is one contiguous 64 KB block) instead of one row-major [M][Nc] ([M][K]) matrix
+  int c_slab, a_slab;
 };
 
 template <int EPI>
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 
-// Self-attention of all heads on mma.sync tensor cores (mha_mma.cu): qkv [B*n][384] -> heads [B*n][128].
-int launch_mha_mma(const float* qkv, int B, int n, float* heads, cudaStream_t st);
+// Self-attention of all heads on mma.sync tensor cores (mha_mma.cu): qkv [B*n][384] (or slab-major [3][B*n][128]) -> heads [B*n][128].
+int launch_mha_mma(const float* qkv, bool slab_major, int B, int n, float* heads, cudaStream_t st);
 
 }  // namespace agh

@@ -23,15 +23,30 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace agh {
 
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 32;             // BK fp32 = 128 bytes = one swizzle-128B row
-constexpr int BLK = BM * BK * 4;                       // one [128 x 32] fp32 block = 16 KB
-constexpr int STAGES = 3;
+// AGH_TC_F16 = 1 (shipped): the operands are split into TWO FP16 values, x = hi + lo' / 2048 with hi = rn_f16(x) and
+// lo' = rn_f16((x - hi) * 2048): the same 11 + 11 significant bits as the TF32 split, but tcgen05.mma.kind::f16 multiplies
+// K = 16 per instruction at twice the tf32 rate (half the MMA count and half the read-modify-write passes over the TMEM
+// accumulator per tile) and the split operands take half the shared memory, which buys a deeper TMA ring.  The
+// remainder is pre-scaled by 2^11 so that it stays a NORMAL fp16 number for every |x| >= 2^-14 (no precision is lost
+// to fp16's narrow exponent range); the cross-term accumulator is scaled back by 2^-11 in the epilogue (exact).
+// Domain: |x| < 65504 (activations after BatchNorm / ReLU and weights are orders of magnitude below; the conversion
+// saturates instead of producing inf).  AGH_TC_F16 = 0 selects the 3xTF32 form the scheme was validated against.
+#ifndef AGH_TC_F16
+#define AGH_TC_F16 1
+#endif
+constexpr bool F16 = AGH_TC_F16 != 0;
+constexpr int BM = 128, BN = 128, BK = 32;             // TMA box: BK fp32 = 128 bytes = one swizzle-128B row
+constexpr int BLK = BM * BK * 4;                       // one [128 x 32] fp32 block = one [128 x 64] fp16 block = 16 KB
+constexpr int KST = F16 ? 2 * BK : BK;                 // K extent of one pipeline stage (F16: two raw boxes -> one hi + one lo' block)
+constexpr int STAGES_WRES = F16 ? 4 : 3, STAGES_STREAM = 3;
+constexpr float CROSS_SCALE = F16 ? 1.0f / 2048.0f : 1.0f;
 constexpr int EPI_WARPS = 8;                          // two per TMEM lane quarter, each takes half of the column chunks
 constexpr int NTHREADS = 192 + 32 * EPI_WARPS;
 
@@ -91,15 +106,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return d;
 }
 // kind::tf32, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor)
+// (a/b format field: kind::tf32 2 = TF32; kind::f16 0 = F16)
 __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+  return (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
+#if AGH_TC_F16
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+#else
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+#endif
       "}\n" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -153,12 +173,46 @@ __device__ __forceinline__ void split_block(unsigned char* hi_ptr, unsigned char
   }
 }
 
+// FP16 split of one stage, in place: `r0` / `r1` hold the raw fp32 boxes of k = 0..31 / 32..63 as TMA wrote them (128-byte
+// rows, 16-byte chunk c of row r at chunk c ^ (r & 7): SWIZZLE_128B); afterwards r0 is the K-major SWIZZLE_128B fp16
+// block of the hi parts ([128 rows][64 halfs]) and r1 that of the scaled remainders.  Thread t owns row t of both boxes,
+// reads all of it before it writes any of it, and the swizzle makes every LDS.128 / STS.128 conflict-free.
+__device__ __forceinline__ void split_f16_row(unsigned char* r0, unsigned char* r1, int t) {
+  const int x = t & 7;
+  unsigned char* p0 = r0 + t * 128;
+  unsigned char* p1 = r1 + t * 128;
+  float4 v[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    v[c] = *reinterpret_cast<const float4*>(p0 + ((c ^ x) << 4));
+    v[8 + c] = *reinterpret_cast<const float4*>(p1 + ((c ^ x) << 4));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {                 // fp16 chunk j = k 8j .. 8j+7 = fp32 chunks 2j, 2j+1
+    const float f[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w, v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint32_t h2;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(f[2 * e + 1]), "f"(f[2 * e]));      // {hi half, lo half} = {b, a}
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+      const float d0 = (f[2 * e] - hf.x) * 2048.0f, d1 = (f[2 * e + 1] - hf.y) * 2048.0f;
+      uint32_t l2;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
+      hw[e] = h2; lw[e] = l2;
+    }
+    *reinterpret_cast<uint4*>(p0 + ((j ^ x) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(p1 + ((j ^ x) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
 // WRES = true : K == 128, W slab resident (hi 64 KB + lo 64 KB), stage = A hi|lo (32 KB), 2 TMEM buffers of {main, cross}
 // WRES = false: K % 32 == 0, stage = A hi|lo + W hi|lo (64 KB), 1 TMEM buffer of {3 main, cross}
 template <bool WRES>
 struct Cfg {
-  static constexpr int STAGE_BYTES = WRES ? 2 * BLK : 4 * BLK;
-  static constexpr int WRES_BYTES = WRES ? 8 * BLK : 0;
+  static constexpr int STAGES = WRES ? STAGES_WRES : STAGES_STREAM;
+  static constexpr int STAGE_BYTES = WRES ? 2 * BLK : 4 * BLK;      // F16: the same bytes hold twice the K extent
+  static constexpr int WRES_BYTES = WRES ? (F16 ? 4 : 8) * BLK : 0;
   static constexpr int NACC = WRES ? 1 : 3;
 #ifndef AGH_TC_NBUF
 #define AGH_TC_NBUF 2
@@ -195,7 +249,7 @@ __host__ __device__ constexpr bool epi_transposed(int epi) { return (AGH_TC_TRAN
 // the other epilogues): decoder projection 736 vs 830 us, but QKV 646 vs 608, FF1 923 vs 812, out-proj 377 vs 292,
 // FF2 1024 vs 968 -- the shuffles were not what bounds those shapes -- so only the decoder projection uses it.
 #ifndef AGH_TC_SWAP_MASK
-#define AGH_TC_SWAP_MASK 0x8
+#define AGH_TC_SWAP_MASK 0xb
 #endif
 __host__ __device__ constexpr bool epi_swap(int epi) { return (AGH_TC_SWAP_MASK >> epi) & 1; }
 #ifndef AGH_TC_FRAG_MASK
@@ -223,6 +277,7 @@ template <int EPI, bool WRES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
   using C = Cfg<WRES>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ unsigned char smem_raw[];
   // swizzle-128B tiles need 1024-byte alignment
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -242,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
-  const int nkb = g.K / BK;
+  const int nkb = g.K / KST;
   const int num_mt = (g.M + BM - 1) / BM;
 
   // The epilogue's per-column vectors are constant for the CTA: staged once, so that no global-memory latency sits
@@ -285,15 +340,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem_u32(wres + kb * BLK), &tmW, bar_wraw, kb * BK, n0);
       }
       uint32_t it = 0;
+      // A coordinates of the box at k0: row-major (k0, row); slab-major input (a_slab: K/128 matrices [M][128] stacked
+      // in one [K/128 * M][128] map) (k0 % 128, (k0 / 128) * M + row) -- rows past M of a slab then come from the next
+      // slab, which only feeds output rows >= M that are never stored
+      auto load_a = [&](uint32_t dst, uint32_t bar, int k0, int row) {
+        if (g.a_slab) tma_load_2d(dst, &tmA, bar, k0 & (BN - 1), (k0 >> 7) * g.M + row);
+        else tma_load_2d(dst, &tmA, bar, k0, row);
+      };
       for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_empty(s), ((it / STAGES) & 1) ^ 1);
           TR(0, it);
           unsigned char* st = ring + s * C::STAGE_BYTES;
-          mbar_expect_tx(bar_raw(s), WRES ? BLK : 2 * BLK);
-          tma_load_2d(smem_u32(st), &tmA, bar_raw(s), kb * BK, mt * BM);
-          if (!WRES) tma_load_2d(smem_u32(st + 2 * BLK), &tmW, bar_raw(s), kb * BK, n0);
+          if (F16) {      // two raw boxes per operand: k = kb*64 .. +31 and +32 .. +63
+            mbar_expect_tx(bar_raw(s), WRES ? 2 * BLK : 4 * BLK);
+            load_a(smem_u32(st), bar_raw(s), kb * KST, mt * BM);
+            load_a(smem_u32(st + BLK), bar_raw(s), kb * KST + BK, mt * BM);
+            if (!WRES) {
+              tma_load_2d(smem_u32(st + 2 * BLK), &tmW, bar_raw(s), kb * KST, n0);
+              tma_load_2d(smem_u32(st + 3 * BLK), &tmW, bar_raw(s), kb * KST + BK, n0);
+            }
+          } else {
+            mbar_expect_tx(bar_raw(s), WRES ? BLK : 2 * BLK);
+            load_a(smem_u32(st), bar_raw(s), kb * BK, mt * BM);
+            if (!WRES) tma_load_2d(smem_u32(st + 2 * BLK), &tmW, bar_raw(s), kb * BK, n0);
+          }
         }
       }
     }
@@ -318,11 +390,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           TR(3, it);
           const uint32_t st = smem_u32(ring + s * C::STAGE_BYTES);
           const uint64_t da_hi = umma_desc(st), da_lo = umma_desc(st + BLK);
-          const uint32_t wb = WRES ? smem_u32(wres + kb * BLK) : st + 2 * BLK;
-          const uint64_t dw_hi = umma_desc(wb), dw_lo = umma_desc(wb + (WRES ? 4 * BLK : BLK));
+          // resident W: TF32 [4 hi blocks][4 lo blocks]; F16 [hi, lo'] pairs, one pair per 64 of K
+          const uint32_t wb = WRES ? smem_u32(wres + (F16 ? 2 * kb : kb) * BLK) : st + 2 * BLK;
+          const uint64_t dw_hi = umma_desc(wb), dw_lo = umma_desc(wb + ((WRES && !F16) ? 4 * BLK : BLK));
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 8 tf32 = 32 bytes inside the swizzle atom
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 8 tf32 = 16 fp16 = 32 bytes inside the swizzle atom
             const int ks = kb * (BK / 8) + k;
             const uint32_t t_cross = t_acc + C::NACC * BN;
             const uint32_t t_main = t_acc + (ks % C::NACC) * BN;
@@ -348,7 +421,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int t = threadIdx.x - 64;
     if (WRES) {
       mbar_wait(bar_wraw, 0);
-      split_block(wres, wres + 4 * BLK, 4 * BLK / 16, t);
+      if (F16) {
+        split_f16_row(wres, wres + BLK, t);
+        split_f16_row(wres + 2 * BLK, wres + 3 * BLK, t);
+      } else {
+        split_block(wres, wres + 4 * BLK, 4 * BLK / 16, t);
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar_wsplit);
     }
@@ -359,8 +437,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(bar_raw(s), (it / STAGES) & 1);
         if (t == 0) TR(1, it);
         unsigned char* st = ring + s * C::STAGE_BYTES;
-        split_block(st, st + BLK, BLK / 16, t);
-        if (!WRES) split_block(st + 2 * BLK, st + 3 * BLK, BLK / 16, t);
+        if (F16) {
+          split_f16_row(st, st + BLK, t);
+          if (!WRES) split_f16_row(st + 2 * BLK, st + 3 * BLK, t);
+        } else {
+          split_block(st, st + BLK, BLK / 16, t);
+          if (!WRES) split_block(st + 2 * BLK, st + 3 * BLK, BLK / 16, t);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(bar_split(s));
         if (t == 0) TR(2, it);
@@ -378,6 +461,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (EPI == EPI_DEC) {
       Cb = (blockIdx.y < 3 ? g.keys + (size_t)blockIdx.y * g.M * D : g.psc) - n0;
       ldc = D;
+    } else if (g.c_slab) {      // slab-major output: this CTA's 128 columns are their own [M][128] matrix
+      Cb = g.C + (size_t)blockIdx.y * g.M * BN - n0;
+      ldc = BN;
     }
     constexpr int CH_PER_WARP = (BN / 32) / (EPI_WARPS / 4);
     uint32_t tile = 0;
@@ -400,7 +486,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         if (EPI == EPI_RES_BN) load_res_sw(r_first);            // independent of the MMAs: issued before the accumulator is ready
         mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
-      if (warp == 6 && lane == 0) TR(5, tile);
         if (warp == 6 && lane == 0) TR(5, tile);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t_acc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
@@ -418,14 +503,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tmem_ld32(t_acc + (uint32_t)(a * BN + rc), ra);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] += __uint_as_float(ra[i]);
+              for (int i = 0; i < 32; ++i) r[i] = fmaf(__uint_as_float(ra[i]), a == C::NACC ? CROSS_SCALE : 1.0f, r[i]);
             }
           }
           if (rc == r_last) {             // all of this warp's share of the accumulator set is in registers: hand it back
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty(ab));
-          if (warp == 6 && lane == 0) TR(6, tile);
             if (warp == 6 && lane == 0) TR(6, tile);
           }
 #ifdef AGH_TC_SKIP_EPILOGUE
@@ -496,14 +580,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tmem_ld16x256b_x4(ta + (uint32_t)(a * BN), ra);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-              for (int i = 0; i < 16; ++i) r[hh * 16 + i] += __uint_as_float(ra[i]);
+              for (int i = 0; i < 16; ++i) r[hh * 16 + i] = fmaf(__uint_as_float(ra[i]), a == C::NACC ? CROSS_SCALE : 1.0f, r[hh * 16 + i]);
             }
           }
           if (c0 == c_last) {             // all of this warp's columns of the accumulator set are in registers: hand it back
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty(ab));
-          if (warp == 6 && lane == 0) TR(6, tile);
             if (warp == 6 && lane == 0) TR(6, tile);
           }
 #ifdef AGH_TC_SKIP_EPILOGUE
@@ -551,7 +634,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(t_acc + (uint32_t)(a * BN + c0), ra);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] += __uint_as_float(ra[i]);
+            for (int i = 0; i < 32; ++i) r[i] = fmaf(__uint_as_float(ra[i]), a == C::NACC ? CROSS_SCALE : 1.0f, r[i]);
           }
         }
         if (c0 == c_last) {               // all of this warp's columns of the accumulator set are in registers: hand it back
@@ -699,7 +782,8 @@ template <int EPI, bool WRES>
 static int launch_cfg(const GemmArgs& g, cudaStream_t st) {
   using C = Cfg<WRES>;
   CUtensorMap tmA, tmW;
-  int rc = make_map(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda);
+  int rc = g.a_slab ? make_map(&tmA, g.A, (uint64_t)g.M * (uint64_t)(g.K / BN), (uint64_t)BN, (uint64_t)BN)
+                    : make_map(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda);
   if (rc) return rc;
   rc = make_map(&tmW, g.Wt, (uint64_t)g.Nc, (uint64_t)g.K, (uint64_t)g.K);
   if (rc) return rc;
@@ -719,7 +803,7 @@ static int launch_cfg(const GemmArgs& g, cudaStream_t st) {
 
 template <int EPI>
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
-  if (g.K % tc::BK != 0 || (g.lda % 4) != 0 || g.Nc % tc::BN != 0 || g.M <= 0) {
+  if (g.K % tc::KST != 0 || (g.lda % 4) != 0 || g.Nc % tc::BN != 0 || g.M <= 0) {
     set_error("gemm_tc: unsupported M=%d K=%d Nc=%d lda=%d", g.M, g.K, g.Nc, g.lda);
     return AGH_E_UNSUPPORTED;
   }

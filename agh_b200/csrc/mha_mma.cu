@@ -217,13 +217,13 @@ __host__ __device__ inline size_t ws_smem_bytes(int n, int npad) {
 }
 
 template <int CH, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) mha_ws_kernel(const float* __restrict__ qkv, int n, int mt,
+__global__ void __launch_bounds__(MAXT, MINB) mha_ws_kernel(const float* __restrict__ qkv, int rs, size_t ps, int n, int mt,
                                                             float* __restrict__ heads) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nchunk = (n + 8 * CH - 1) / (8 * CH), npad = nchunk * 8 * CH;
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* base = qkv + (size_t)b * n * (3 * D);
+  const float* base = qkv + (size_t)b * n * rs;      // row j, part p (Q/K/V), column c at base + j * rs + p * ps + c
   float* raw_kv = reinterpret_cast<float*>(smem_raw);                       // [2][n][KVS]  raw K_h | V_h rows
   uint2* ring = reinterpret_cast<uint2*>(raw_kv + 2 * n * KVS);             // [2]{ K [npad][KSTR], V [npad/2][VSTR] }
   const int ring_pairs = npad * KSTR + (npad / 2) * VSTR;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_ws_kernel(const float* __restr
       float* dst = raw_kv + (h & 1) * n * KVS;
       for (int idx = lane; idx < n * 8; idx += 32) {
         const int j = idx >> 3, c = idx & 7;
-        cp_async16(dst + j * KVS + c * 4, base + (size_t)j * 3 * D + (1 + (c >> 2)) * D + h * HD + (c & 3) * 4);
+        cp_async16(dst + j * KVS + c * 4, base + (size_t)j * rs + (size_t)(1 + (c >> 2)) * ps + h * HD + (c & 3) * 4);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_ws_kernel(const float* __restr
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int r = (e & 1) ? r1 : r0;
-          q[ks][e] = (r < n) ? __ldg(base + (size_t)r * 3 * D + h * HD + ks * 8 + t + ((e & 2) ? 4 : 0)) : 0.f;
+          q[ks][e] = (r < n) ? __ldg(base + (size_t)r * rs + h * HD + ks * 8 + t + ((e & 2) ? 4 : 0)) : 0.f;
         }
       }
     };
@@ -304,7 +304,7 @@ __host__ __device__ inline size_t lane_bytes(int npad) {
 }
 
 template <int CH, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __restrict__ qkv, int n, int hpc, int mt,
+__global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __restrict__ qkv, int rs, size_t ps, int n, int hpc, int mt,
                                                              float* __restrict__ heads) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nchunk = (n + 8 * CH - 1) / (8 * CH), npad = nchunk * 8 * CH;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __rest
   const int g = lane >> 2, t = lane & 3;
   const int hl = warp / mt, mi = warp - hl * mt;
   const int lt = threadIdx.x - hl * mt * 32, lthreads = mt * 32;
-  const float* base = qkv + (size_t)b * n * (3 * D);
+  const float* base = qkv + (size_t)b * n * rs;      // row j, part p (Q/K/V), column c at base + j * rs + p * ps + c
   float* raw = reinterpret_cast<float*>(smem_raw + hl * lane_bytes(npad));
   uint2* ksp = reinterpret_cast<uint2*>(raw + npad * RAWS);
   uint2* vsp = ksp + npad * KSTR;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __rest
   auto issue_load = [&](int h) {            // rows [0, n) of Q_h | K_h | V_h, 12 chunks of 16 bytes per row
     for (int idx = lt; idx < n * 12; idx += lthreads) {
       const int j = idx / 12, c = idx - j * 12;
-      cp_async16(raw + j * RAWS + c * 4, base + (size_t)j * 3 * D + (c >> 2) * D + h * HD + (c & 3) * 4);
+      cp_async16(raw + j * RAWS + c * 4, base + (size_t)j * rs + (size_t)(c >> 2) * ps + h * HD + (c & 3) * 4);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __rest
 }
 
 template <int CH, int MAXT, int MINB>
-int launch_uniform(const float* qkv, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
+int launch_uniform(const float* qkv, int rs, size_t ps, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
   const int npad = ceil_div(n, 8 * CH) * 8 * CH;
   const size_t smem = (size_t)hpc * lane_bytes(npad);
   static size_t smem_set = 0;
@@ -361,13 +361,13 @@ int launch_uniform(const float* qkv, int B, int n, int hpc, int mt, float* heads
     AGH_CUDA(cudaFuncSetAttribute(mha_mma_kernel<CH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  mha_mma_kernel<CH, MAXT, MINB><<<B, hpc * mt * 32, smem, st>>>(qkv, n, hpc, mt, heads);
+  mha_mma_kernel<CH, MAXT, MINB><<<B, hpc * mt * 32, smem, st>>>(qkv, rs, ps, n, hpc, mt, heads);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
 }
 
 template <int CH, int MAXT, int MINB>
-int launch_ws(const float* qkv, int B, int n, int mt, float* heads, cudaStream_t st) {
+int launch_ws(const float* qkv, int rs, size_t ps, int B, int n, int mt, float* heads, cudaStream_t st) {
   const int npad = ceil_div(n, 8 * CH) * 8 * CH;
   const size_t smem = ws_smem_bytes(n, npad);
   static size_t smem_set = 0;
@@ -375,27 +375,30 @@ int launch_ws(const float* qkv, int B, int n, int mt, float* heads, cudaStream_t
     AGH_CUDA(cudaFuncSetAttribute(mha_ws_kernel<CH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  mha_ws_kernel<CH, MAXT, MINB><<<B, (mt + 1) * 32, smem, st>>>(qkv, n, mt, heads);
+  mha_ws_kernel<CH, MAXT, MINB><<<B, (mt + 1) * 32, smem, st>>>(qkv, rs, ps, n, mt, heads);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
 }
 
 // CTAs of up to 8 warps (N <= 111 with the producer warp) may use up to 128 registers; larger graphs need up to 20.
 template <int CH>
-int launch_ch(const float* qkv, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
+int launch_ch(const float* qkv, int rs, size_t ps, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
   static const bool no_ws = getenv("AGH_MHA_WS") != nullptr && atoi(getenv("AGH_MHA_WS")) == 0;
   const int npad = ceil_div(n, 8 * CH) * 8 * CH;
   if (!no_ws && hpc == 1 && ws_smem_bytes(n, npad) <= 227 * 1024) {
-    if (mt + 1 <= 8) return launch_ws<CH, 256, 2>(qkv, B, n, mt, heads, st);
-    return launch_ws<CH, MHA_MAX_THREADS, 1>(qkv, B, n, mt, heads, st);
+    if (mt + 1 <= 8) return launch_ws<CH, 256, 2>(qkv, rs, ps, B, n, mt, heads, st);
+    return launch_ws<CH, MHA_MAX_THREADS, 1>(qkv, rs, ps, B, n, mt, heads, st);
   }
-  if (hpc * mt <= 8) return launch_uniform<CH, 256, 2>(qkv, B, n, hpc, mt, heads, st);
-  return launch_uniform<CH, MHA_MAX_THREADS, 1>(qkv, B, n, hpc, mt, heads, st);
+  if (hpc * mt <= 8) return launch_uniform<CH, 256, 2>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+  return launch_uniform<CH, MHA_MAX_THREADS, 1>(qkv, rs, ps, B, n, hpc, mt, heads, st);
 }
 
 }  // namespace
 
-int launch_mha_mma(const float* qkv, int B, int n, float* heads, cudaStream_t st) {
+int launch_mha_mma(const float* qkv, bool slab_major, int B, int n, float* heads, cudaStream_t st) {
+  // row-major [B*n][384] rows Q|K|V, or slab-major: three [B*n][128] matrices (the tensor-core QKV GEMM's output form)
+  const int rs = slab_major ? D : 3 * D;
+  const size_t ps = slab_major ? (size_t)B * n * D : (size_t)D;
   const int mt = ceil_div(n, 16);
   int hpc = 1;
   while (hpc < H && 2 * hpc * mt <= 8) hpc *= 2;                 // about 8 warps per CTA for small graphs
@@ -408,12 +411,12 @@ int launch_mha_mma(const float* qkv, int B, int n, float* heads, cudaStream_t st
     if (cost < best_cost) { best = ch; best_cost = cost; }
   }
   switch (best) {
-    case 3: return launch_ch<3>(qkv, B, n, hpc, mt, heads, st);
-    case 4: return launch_ch<4>(qkv, B, n, hpc, mt, heads, st);
-    case 5: return launch_ch<5>(qkv, B, n, hpc, mt, heads, st);
-    case 6: return launch_ch<6>(qkv, B, n, hpc, mt, heads, st);
-    case 7: return launch_ch<7>(qkv, B, n, hpc, mt, heads, st);
-    default: return launch_ch<8>(qkv, B, n, hpc, mt, heads, st);
+    case 3: return launch_ch<3>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    case 4: return launch_ch<4>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    case 5: return launch_ch<5>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    case 6: return launch_ch<6>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    case 7: return launch_ch<7>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    default: return launch_ch<8>(qkv, rs, ps, B, n, hpc, mt, heads, st);
   }
 }
 
