@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include <math_constants.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace agh {
@@ -35,8 +36,24 @@ namespace {
 
 constexpr int RAWS = 52;          // mha_mma_kernel raw row stride in floats: Q 16 | K 16 | V 16 | pad 4
 constexpr int KVS = 36;           // mha_ws_kernel raw K|V row stride in floats: K 16 | V 16 | pad 4
+// AGH_MHA_F16 = 1 (shipped): the same two-term FP16 split as the tcgen05 GEMM (x = hi + lo' / 2048, gemm_tc.cu) on
+// mma.sync.m16n8k16: one instruction covers the whole head dimension of S = Q K^T and 16 keys of P V, i.e. HALF the
+// tensor instructions of the m16n8k8 TF32 form at the same 11 + 11 significant bits.  AGH_MHA_F16 = 0 keeps the
+// 3xTF32 form the scheme was validated against.
+#ifndef AGH_MHA_F16
+#define AGH_MHA_F16 1
+#endif
+#if AGH_MHA_F16
+constexpr int KSTR = 12;          // split K row (one key), uint2 units: 4 hi {d2t,d2t+1 | d2t+8,d2t+9}, 4 lo', 4 pad (96 B: conflict-free)
+constexpr int VGRP = 128;         // split V, per 16 keys: [d = 0,1][g = 0..7][t = 0..3] hi {keys 2t,2t+1 | 2t+8,2t+9} of dim 8d+g (64 units), then lo'
+constexpr int KEY_PAIR = 2;       // chunk lengths are even: P V consumes the score tiles in pairs (16 keys per mma)
+__host__ __device__ inline size_t split_bytes(int npad) { return (size_t)npad * KSTR * 8 + (size_t)(npad / 16) * VGRP * 8; }
+#else
 constexpr int KSTR = 20;          // split K row (one key): 8 hi pairs, 8 lo pairs, 4 pad
 constexpr int VSTR = 36;          // split V row (two keys): 16 hi pairs, 16 lo pairs, 4 pad
+constexpr int KEY_PAIR = 1;
+__host__ __device__ inline size_t split_bytes(int npad) { return (size_t)npad * KSTR * 8 + (size_t)(npad / 2) * VSTR * 8; }
+#endif
 constexpr int MHA_MAX_THREADS = 640;
 // norm_factor = 1/sqrt(16) (graph_encoder.py:40,89) and log2(e) go into q once: the softmax runs in base 2
 constexpr float QSCALE = 0.25f * 1.4426950408889634f;
@@ -81,6 +98,158 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+#if AGH_MHA_F16
+struct QFrag { uint32_t hi[4], lo[4]; };
+__device__ __forceinline__ uint32_t pack_f16(float lo_elem, float hi_elem) {        // {lower half, upper half}
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t h2) { return __half22float2(*reinterpret_cast<const __half2*>(&h2)); }
+// (a, b) -> hi = f16x2(a, b), lo' = f16x2((a - hi_a) 2^11, (b - hi_b) 2^11)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16(a, b);
+  const float2 hf = unpack_f16(hi);
+  lo = pack_f16((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+// this lane's A fragment of 16 query rows x 16 dims from its 8 raw elements q[i] = {row r0 | r1}[i & 1], dims 2t + 8 (i >> 1) + {0, 1}
+__device__ __forceinline__ void make_qfrag(const float2 (&q)[4], QFrag& f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_pair(q[i].x * QSCALE, q[i].y * QSCALE, f.hi[i], f.lo[i]);
+}
+// K_h / V_h rows [0, npad) (zeros beyond n) -> fragment-ordered FP16 (hi, lo') words; `raw` rows hold K at koff, V at voff
+__device__ __forceinline__ void split_kv(const float* raw, int rstride, int koff, int voff, int n, int npad, uint2* ksp,
+                                         uint2* vsp, int tid, int nthreads) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = tid; j < npad; j += nthreads) {                      // K: one key per thread
+    const float4* src = reinterpret_cast<const float4*>(raw + j * rstride + koff);
+    const bool ok = j < n;
+    const float4 v0 = ok ? src[0] : z, v1 = ok ? src[1] : z, v2 = ok ? src[2] : z, v3 = ok ? src[3] : z;
+    const float d[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+    uint32_t hw[8], lw[8];                                          // word 2t: dims 2t, 2t+1; word 2t+1: dims 2t+8, 2t+9
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      split_pair(d[2 * t], d[2 * t + 1], hw[2 * t], lw[2 * t]);
+      split_pair(d[2 * t + 8], d[2 * t + 9], hw[2 * t + 1], lw[2 * t + 1]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(ksp + j * KSTR);
+    dst[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); dst[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    dst[2] = make_uint4(lw[0], lw[1], lw[2], lw[3]); dst[3] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+  }
+  uint32_t* vw = reinterpret_cast<uint32_t*>(vsp);
+  for (int idx = tid; idx < npad * 2; idx += nthreads) {            // V: (keys 2 kp, 2 kp + 1; dims 4 c .. 4 c + 3)
+    const int kp = idx >> 2, c = idx & 3;
+    const float4 a = (2 * kp < n) ? *reinterpret_cast<const float4*>(raw + (2 * kp) * rstride + voff + c * 4) : z;
+    const float4 b = (2 * kp + 1 < n) ? *reinterpret_cast<const float4*>(raw + (2 * kp + 1) * rstride + voff + c * 4) : z;
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    const int kg = kp >> 3, pp = kp & 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int dd = 4 * c + i;
+      const int unit = kg * VGRP + (dd * 4) + (pp & 3);             // ((d * 8 + g) * 4 + t) with dd = 8 d + g
+      uint32_t hi, lo;
+      split_pair(av[i], bv[i], hi, lo);
+      vw[unit * 2 + (pp >> 2)] = hi;
+      vw[(unit + 64) * 2 + (pp >> 2)] = lo;
+    }
+  }
+}
+
+// One warp, 16 query rows (fragment q), all keys of one head: out[d][e] = normalised O in the mma C layout
+// (e = 0,1: row r0, dims 8d + 2t, +1;  e = 2,3: row r0 + 8).  kr / vr point at this lane's first K / V fragment.
+template <int CH>
+__device__ __forceinline__ void attend(const uint2* kr, const uint2* vr, const QFrag& q, int n, int nchunk, int t,
+                                       float (&out)[2][4]) {
+  static_assert(CH % 2 == 0, "score tiles are consumed in pairs");
+  constexpr float CS = 1.0f / 2048.0f;
+  // O accumulators, dims [0,8) and [8,16): main product and the two (2^11-scaled) cross products
+  float om[2][4], ox[2][4], oy[2][4];
+#pragma unroll
+  for (int d = 0; d < 2; ++d)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { om[d][e] = 0.f; ox[d][e] = 0.f; oy[d][e] = 0.f; }
+  float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+
+  for (int c = 0; c < nchunk; ++c, kr += CH * 8 * KSTR, vr += (CH / 2) * VGRP) {
+    float s[CH][4];
+    // ---- S = Q K^T for 8 CH keys: one k16 mma per product ----
+#pragma unroll
+    for (int jt = 0; jt < CH; ++jt) {
+      const uint2* kt = kr + jt * 8 * KSTR;
+      const uint2 kh = kt[0], kl = kt[4];
+      float sx[4] = {0.f, 0.f, 0.f, 0.f};
+      s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
+      mma_f16(sx, q.lo, kh);
+      mma_f16(sx, q.hi, kl);
+      mma_f16(s[jt], q.hi, kh);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[jt][e] = fmaf(sx[e], CS, s[jt][e]);
+    }
+    if ((c + 1) * CH * 8 > n) {             // the chunk holds padding keys: mask them (a warp-uniform skip of the full
+#pragma unroll                              // tiles measured 4 % slower: it breaks the schedule across tiles)
+      for (int jt = 0; jt < CH; ++jt) {
+        const int key = (c * CH + jt) * 8 + 2 * t;
+        if (key >= n) { s[jt][0] = -CUDART_INF_F; s[jt][2] = -CUDART_INF_F; }
+        if (key + 1 >= n) { s[jt][1] = -CUDART_INF_F; s[jt][3] = -CUDART_INF_F; }
+      }
+    }
+    // ---- online softmax: raise the running maxima of rows r0 / r0 + 8 ----
+    float x0 = -CUDART_INF_F, x1 = -CUDART_INF_F;
+#pragma unroll
+    for (int jt = 0; jt < CH; ++jt) {
+      x0 = fmaxf(x0, fmaxf(s[jt][0], s[jt][1]));
+      x1 = fmaxf(x1, fmaxf(s[jt][2], s[jt][3]));
+    }
+    x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+    const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);        // finite: every chunk holds a valid key
+    if (c > 0) {
+      const float f0 = ex2(m0 - n0), f1 = ex2(m1 - n1);
+      l0 *= f0; l1 *= f1;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        om[d][0] *= f0; om[d][1] *= f0; ox[d][0] *= f0; ox[d][1] *= f0; oy[d][0] *= f0; oy[d][1] *= f0;
+        om[d][2] *= f1; om[d][3] *= f1; ox[d][2] *= f1; ox[d][3] *= f1; oy[d][2] *= f1; oy[d][3] *= f1;
+      }
+    }
+    m0 = n0; m1 = n1;
+    // ---- O += P V, 16 keys per mma: the two score tiles of a pair ARE the A fragment (rows g / g+8, keys 2t,2t+1 | 2t+8,2t+9) ----
+#pragma unroll
+    for (int jp = 0; jp < CH / 2; ++jp) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int jt = 2 * jp + u;
+        const float p0 = ex2(s[jt][0] - m0), p1 = ex2(s[jt][1] - m0), p2 = ex2(s[jt][2] - m1), p3 = ex2(s[jt][3] - m1);
+        l0 += p0 + p1; l1 += p2 + p3;
+        split_pair(p0, p1, ph[2 * u], pl[2 * u]);
+        split_pair(p2, p3, ph[2 * u + 1], pl[2 * u + 1]);
+      }
+      const uint2* vt = vr + jp * VGRP;
+      const uint2 vh0 = vt[0], vh1 = vt[32], vl0 = vt[64], vl1 = vt[96];
+      mma_f16(om[0], ph, vh0);
+      mma_f16(om[1], ph, vh1);
+      mma_f16(ox[0], pl, vh0);
+      mma_f16(ox[1], pl, vh1);
+      mma_f16(oy[0], ph, vl0);
+      mma_f16(oy[1], ph, vl1);
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    out[d][0] = fmaf(ox[d][0] + oy[d][0], CS, om[d][0]) * i0; out[d][1] = fmaf(ox[d][1] + oy[d][1], CS, om[d][1]) * i0;
+    out[d][2] = fmaf(ox[d][2] + oy[d][2], CS, om[d][2]) * i1; out[d][3] = fmaf(ox[d][3] + oy[d][3], CS, om[d][3]) * i1;
+  }
+}
+#else
 // (a_i, b_i), i = 0..3  ->  4 hi pairs at dst[0..3], 4 lo pairs at dst[lo_off..lo_off+3]
 __device__ __forceinline__ void store_pairs(uint2* dst, int lo_off, const float4 a, const float4 b) {
   uint32_t ah[4], al[4], bh[4], bl[4];
@@ -200,6 +369,8 @@ __device__ __forceinline__ void attend(const uint2* kr, const uint2* vr, const u
   }
 }
 
+#endif
+
 __device__ __forceinline__ void store_rows(float* heads_bh, int n, int r0, int t, const float (&out)[2][4]) {
   // heads_bh = heads + b * n * D + h * HD
 #pragma unroll
@@ -213,7 +384,7 @@ __device__ __forceinline__ void store_rows(float* heads_bh, int n, int r0, int t
 // warp-specialised kernel: grid = B CTAs, block = (mt + 1) warps; warps 0..mt-1 compute, warp mt produces
 // ------------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t ws_smem_bytes(int n, int npad) {
-  return 2 * (size_t)n * KVS * 4 + 2 * ((size_t)npad * KSTR * 8 + (size_t)(npad / 2) * VSTR * 8) + 64;
+  return 2 * (size_t)n * KVS * 4 + 2 * split_bytes(npad) + 64;
 }
 
 template <int CH, int MAXT, int MINB>
@@ -226,7 +397,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_ws_kernel(const float* __restr
   const float* base = qkv + (size_t)b * n * rs;      // row j, part p (Q/K/V), column c at base + j * rs + p * ps + c
   float* raw_kv = reinterpret_cast<float*>(smem_raw);                       // [2][n][KVS]  raw K_h | V_h rows
   uint2* ring = reinterpret_cast<uint2*>(raw_kv + 2 * n * KVS);             // [2]{ K [npad][KSTR], V [npad/2][VSTR] }
-  const int ring_pairs = npad * KSTR + (npad / 2) * VSTR;
+  const int ring_pairs = (int)(split_bytes(npad) / 8);
   uint64_t* split_full = reinterpret_cast<uint64_t*>(ring + 2 * ring_pairs);
   uint64_t* split_empty = split_full + 2;
 
@@ -263,6 +434,16 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_ws_kernel(const float* __restr
     // ================= compute warps =================
     const int g = lane >> 2, t = lane & 3;
     const int r0 = warp * 16 + g, r1 = r0 + 8;
+#if AGH_MHA_F16
+    auto load_q = [&](int h, float2 (&q)[4]) {                       // this lane's A-fragment elements of Q_h
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (i & 1) ? r1 : r0;
+        q[i] = (r < n) ? __ldg(reinterpret_cast<const float2*>(base + (size_t)r * rs + h * HD + 2 * t + 8 * (i >> 1))) : make_float2(0.f, 0.f);
+      }
+    };
+    float2 qraw[4];
+#else
     auto load_q = [&](int h, float (&q)[2][4]) {                     // this lane's A-fragment elements of Q_h
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
@@ -274,19 +455,29 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_ws_kernel(const float* __restr
       }
     };
     float qraw[2][4];
+#endif
     load_q(0, qraw);
     for (int h = 0; h < H; ++h) {
       const int bf = h & 1;
+#if AGH_MHA_F16
+      QFrag qf;
+      make_qfrag(qraw, qf);
+#else
       uint32_t qhi[2][4], qlo[2][4];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
         for (int e = 0; e < 4; ++e) split_rn(qraw[ks][e] * QSCALE, qhi[ks][e], qlo[ks][e]);
+#endif
       if (h + 1 < H) load_q(h + 1, qraw);                            // in flight during this head
       mbar_wait(split_full + bf, (h >> 1) & 1);
       const uint2* ksp = ring + bf * ring_pairs;
       float out[2][4];
+#if AGH_MHA_F16
+      attend<CH>(ksp + g * KSTR + t, ksp + npad * KSTR + g * 4 + t, qf, n, nchunk, t, out);
+#else
       attend<CH>(ksp + g * KSTR + t, ksp + npad * KSTR + t * VSTR + g, qhi, qlo, n, nchunk, t, out);
+#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(split_empty + bf);                  // the ring slot may be refilled
       store_rows(heads + (size_t)b * n * D + h * HD, n, r0, t, out);
@@ -300,7 +491,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_ws_kernel(const float* __restr
 // rows of the next head arrive by cp.async while the current head is computed.
 // ------------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t lane_bytes(int npad) {
-  return (size_t)npad * RAWS * 4 + (size_t)npad * KSTR * 8 + (size_t)(npad / 2) * VSTR * 8;
+  return (size_t)npad * RAWS * 4 + split_bytes(npad);
 }
 
 template <int CH, int MAXT, int MINB>
@@ -333,6 +524,18 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __rest
     const int h = hl + it * hpc;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                        // raw rows of head h visible; previous head's fragments no longer read
+#if AGH_MHA_F16
+    QFrag qf;
+    {
+      float2 qraw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (i & 1) ? r1 : r0;
+        qraw[i] = (r < n) ? *reinterpret_cast<const float2*>(raw + r * RAWS + 2 * t + 8 * (i >> 1)) : make_float2(0.f, 0.f);
+      }
+      make_qfrag(qraw, qf);
+    }
+#else
     uint32_t qhi[2][4], qlo[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
@@ -343,11 +546,16 @@ __global__ void __launch_bounds__(MAXT, MINB) mha_mma_kernel(const float* __rest
         split_rn(q * QSCALE, qhi[ks][e], qlo[ks][e]);
       }
     }
+#endif
     split_kv(raw, RAWS, HD, 2 * HD, n, npad, ksp, vsp, lt, lthreads);
     __syncthreads();                        // fragments visible; raw buffer free for the next head
     if (it + 1 < nit) issue_load(h + hpc);
     float out[2][4];
+#if AGH_MHA_F16
+    attend<CH>(ksp + g * KSTR + t, vsp + g * 4 + t, qf, n, nchunk, t, out);
+#else
     attend<CH>(ksp + g * KSTR + t, vsp + t * VSTR + g, qhi, qlo, n, nchunk, t, out);
+#endif
     store_rows(heads + (size_t)b * n * D + h * HD, n, r0, t, out);
   }
 }
@@ -404,6 +612,24 @@ int launch_mha_mma(const float* qkv, bool slab_major, int B, int n, float* heads
   while (hpc < H && 2 * hpc * mt <= 8) hpc *= 2;                 // about 8 warps per CTA for small graphs
   AGH_CHECK_ARG((hpc * mt + 1) * 32 <= MHA_MAX_THREADS);
   // chunk length: least padded work (about 60 instructions per key fragment, 60 per chunk for the rescale)
+#if AGH_MHA_F16
+  const int ntile = 2 * ceil_div(n, 16);                         // score tiles come in pairs (16 keys per P V mma)
+  // CTAs of more than 8 warps have 102 registers per thread: chunks of at most 8 tiles there (longer ones spill)
+  const int ch_max = (hpc * mt + 1) * 32 <= 256 ? 14 : 8;
+  int best = 8, best_cost = 1 << 30;
+  for (int ch = ch_max; ch >= 4; ch -= 2) {
+    const int chunks = ceil_div(ntile, ch), cost = chunks * ch * 60 + chunks * 60;
+    if (cost < best_cost) { best = ch; best_cost = cost; }
+  }
+  switch (best) {
+    case 4: return launch_ch<4>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    case 6: return launch_ch<6>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    case 8: return launch_ch<8>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    case 10: return launch_ch<10>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    case 12: return launch_ch<12>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+    default: return launch_ch<14>(qkv, rs, ps, B, n, hpc, mt, heads, st);
+  }
+#else
   const int ntile = ceil_div(n, 8);
   int best = 8, best_cost = 1 << 30;
   for (int ch = 8; ch >= 3; --ch) {
@@ -418,6 +644,7 @@ int launch_mha_mma(const float* qkv, bool slab_major, int B, int n, float* heads
     case 7: return launch_ch<7>(qkv, rs, ps, B, n, hpc, mt, heads, st);
     default: return launch_ch<8>(qkv, rs, ps, B, n, hpc, mt, heads, st);
   }
+#endif
 }
 
 }  // namespace agh
