@@ -273,7 +273,7 @@ def run_cuda(args):
             'roofline_encoder': {'kernels': 'gemm_tc_kernel + mha_mma_kernel + init_embed (agh_encode, agh_precompute)',
                                  'bound': 'tensor', 'achieved': enc_tflops, 'peak': tflops, 'unit': 'TFLOP/s',
                                  'frac': enc_tflops / tflops, 'share_of_step': (t_enc + t_pre) / ms_res,
-                                 'note': 'tcgen05 kind::tf32 with the 3xTF32 split (3 MMAs per product) + mma.sync 3xTF32 attention; '
+                                 'note': 'tcgen05 kind::f16 with the two-term FP16 split (3 MMAs per product, fp32-level accuracy) + mma.sync m16n8k16 attention with the same split; '
                                          'achieved counts algorithmic fp32 flops, peak is the measured bf16 cuBLAS figure'},
             'phase_ms': {'encode': t_enc, 'precompute': t_pre, 'decode': t_dec},
             'decode_instance_steps_per_sec': total_inst_steps * ws / (ms_res * 1e-3),

@@ -81,7 +81,7 @@ int agh_chain_tw_left(float* tw_left_levels, int level, const float* serve /*[B]
  *   h_out[B][n][128] f32.  workspace: agh_encoder_workspace_bytes(B,N) bytes.
  */
 size_t agh_encoder_workspace_bytes(int B, int N);
-/* GEMM back end of agh_encode / agh_precompute: 1 = tcgen05 tensor cores with the 3xTF32 split (default),
+/* GEMM back end of agh_encode / agh_precompute: 1 = tcgen05 tensor cores with the two-term FP16 split (default; fp32-level accuracy),
  * 0 = fp32 CUDA-core SGEMM (kept for A/B measurements; env AGH_GEMM=simt selects it at load time) */
 int agh_set_gemm_backend(int backend);
 /* twr_f32: tw_right held f32 values in the caller (fleet 10) -> tw_right/1440 is an f32 division */

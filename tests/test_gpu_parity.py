@@ -407,7 +407,7 @@ def test_training_step_matches_oracle(tables, weights):
 
 @pytest.mark.parametrize('n,B', [(20, 7), (100, 300), (50, 1000)])
 def test_tensor_core_gemm_matches_cuda_core(cuda_model, tables, n, B):
-    """tcgen05 3xTF32 GEMMs and mma.sync 3xTF32 attention (encoder + precompute) against the fp32 CUDA-core path
+    """tcgen05 split-FP16 GEMMs and mma.sync split-FP16 attention (encoder + precompute) against the fp32 CUDA-core path
     and a float64 evaluation: fp32-level agreement,
     including ragged last row tiles (M = B*(n+1) is not a multiple of 128)."""
     from agh_b200 import ops, _lib
@@ -425,7 +425,7 @@ def test_tensor_core_gemm_matches_cuda_core(cuda_model, tables, n, B):
         torch.cuda.synchronize()
     finally:
         lib.agh_set_gemm_backend(1)
-    # 12 chained GEMMs + 3 attentions in 3xTF32; |h| reaches ~13.  Both back ends are judged against a float64
+    # 12 chained GEMMs + 3 attentions with split (hi + lo') operands; |h| reaches ~13.  Both back ends are judged against a float64
     # evaluation of the same layers: the split products carry ~2^-21 relative error each, a few times the fp32 FMA
     # chain's, which stays fp32-level after three layers.
     W64 = {k: v.double() for k, v in cuda_model.state_dict().items()}
