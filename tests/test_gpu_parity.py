@@ -405,7 +405,7 @@ def test_training_step_matches_oracle(tables, weights):
     assert int(model.state_dict()['embedder.layers.0.1.normalizer.num_batches_tracked']) == 10
 
 
-@pytest.mark.parametrize('n,B', [(20, 7), (100, 300), (50, 1000)])
+@pytest.mark.parametrize('n,B', [(20, 7), (100, 300), (50, 1000), (200, 40), (300, 12)])
 def test_tensor_core_gemm_matches_cuda_core(cuda_model, tables, n, B):
     """tcgen05 split-FP16 GEMMs and mma.sync split-FP16 attention (encoder + precompute) against the fp32 CUDA-core path
     and a float64 evaluation: fp32-level agreement,
