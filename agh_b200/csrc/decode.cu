@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   float* s_z = reinterpret_cast<float*>(smem + L.z);
   float* s_serve = reinterpret_cast<float*>(smem + L.serve);
   float* s_o = reinterpret_cast<float*>(smem + L.o);
-  float* s_q = reinterpret_cast<float*>(smem + L.qb);        // query of the current step, written by threads 0..127
+  float* s_q = reinterpret_cast<float*>(smem + L.qb);        // query of the current step, written by threads 128..255
   float* s_red = reinterpret_cast<float*>(smem + L.red);
   uint32_t* s_mw = reinterpret_cast<uint32_t*>(smem + L.mw);
   uint16_t* s_idx = reinterpret_cast<uint16_t*>(smem + L.idx);
@@ -211,12 +211,15 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     s_crd[j] = ok ? (int)a.coord[(size_t)kb * n + j] : 0;
     s_serve[j] = 0.f;
   }
-  // threads 0..127 each own one component of the query: base, capacity and time coefficients in registers
+  // threads 128..255 each own one component of the query (base, capacity and time coefficients in registers): at
+  // N <= 127 the feasibility of the nodes is evaluated by threads 0..127, so the two halves of a step's first phase run
+  // side by side in different warps instead of one after the other in the same ones
+  const int qi = tid - (256 - D);
   float qb_r = 0.f, wc_r = 0.f, wt_r = 0.f;
-  if (tid < D) {
-    qb_r = a.qbase[(size_t)kb * D + tid];
-    wc_r = a.wblob[W_CAP + tid];
-    wt_r = a.wblob[W_TIME + tid];
+  if (qi >= 0) {
+    qb_r = a.qbase[(size_t)kb * D + qi];
+    wc_r = a.wblob[W_CAP + qi];
+    wt_r = a.wblob[W_TIME + qi];
   }
   __syncthreads();
   mbar_wait(bar, 0);
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
 #pragma unroll
   for (int k = 0; k < MPT; ++k) ddm[k] = (tid + 256 * k < n) ? __ldg(a.distance + NODE_SIZE * s_crd[0] + cjm[k]) : 0.f;
   float pv_r = 0.f;
-  if (!(RES & RES_P) && tid < D) pv_r = __ldg(Pm + tid);
+  if (!(RES & RES_P) && qi >= 0) pv_r = __ldg(Pm + qi);
 
   while (replay ? (t < a.replay_steps) : (nvis < n)) {
     float* dc = s_dcur + (t & 1) * NPAD;
@@ -300,10 +303,10 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       const double q0 = cft * inv;
       tf = (float)fma(fma(-q0, 1440.0, cft), inv, q0);
     }
-    // one component of the query per thread (threads 0..127), published through shared memory
-    if (tid < D) {
-      const float pv = (RES & RES_P) ? Pm[(size_t)prev * D + tid] : pv_r;
-      s_q[tid] = fmaf(wt_r, tf, fmaf(wc_r, rem, qb_r + pv));
+    // one component of the query per thread (threads 128..255), published through shared memory
+    if (qi >= 0) {
+      const float pv = (RES & RES_P) ? Pm[(size_t)prev * D + qi] : pv_r;
+      s_q[qi] = fmaf(wt_r, tf, fmaf(wc_r, rem, qb_r + pv));
     }
 
     // (4) feasibility of node tid (+256k): state_agh.py:148-174, exact dtypes; one node per thread, the
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       const int cnext = s_crd[sel];
 #pragma unroll
       for (int k = 0; k < MPT; ++k) ddm[k] = (tid + 256 * k < n) ? __ldg(a.distance + NODE_SIZE * cnext + cjm[k]) : 0.f;
-      if (!(RES & RES_P) && tid < D) pv_r = __ldg(Pm + (size_t)sel * D + tid);
+      if (!(RES & RES_P) && qi >= 0) pv_r = __ldg(Pm + (size_t)sel * D + qi);
     }
     const float g_z = s_z[sel];
     const float logS = logf(S);
