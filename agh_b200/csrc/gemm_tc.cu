@@ -273,7 +273,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TR(role, idx) do { } while (0)
 #endif
 
-template <int EPI, bool WRES>
+// CSLAB: the output is slab-major (Nc/128 separate [M][128] matrices).  A template parameter, like the fixed pitch of
+// the residual epilogue below, so that the row pitch is a compile-time 128: the 32 stores of a chunk then share one
+// base register with immediate offsets instead of 32 64-bit multiply-adds (the epilogue warps are what bounds the tile
+// period of the K = 128 shapes).
+template <int EPI, bool WRES, bool CSLAB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
   using C = Cfg<WRES>;
@@ -461,10 +465,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (EPI == EPI_DEC) {
       Cb = (blockIdx.y < 3 ? g.keys + (size_t)blockIdx.y * g.M * D : g.psc) - n0;
       ldc = D;
-    } else if (g.c_slab) {      // slab-major output: this CTA's 128 columns are their own [M][128] matrix
+    } else if (CSLAB) {         // slab-major output: this CTA's 128 columns are their own [M][128] matrix
       Cb = g.C + (size_t)blockIdx.y * g.M * BN - n0;
       ldc = BN;
+    } else if (EPI == EPI_RES_BN) {
+      ldc = BN;                 // residual + BatchNorm outputs and residuals are [M][128] activations (checked by the launcher)
     }
+    const int ldr = (EPI == EPI_RES_BN) ? BN : g.ldr;
     constexpr int CH_PER_WARP = (BN / 32) / (EPI_WARPS / 4);
     uint32_t tile = 0;
     for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++tile) {
@@ -480,9 +487,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float rs[32];                                           // residual of rows mt*BM + rc + i, this thread's column
         auto load_res_sw = [&](int rc) {
           const int rbase = mt * BM + rc;
-          const float* src = g.res + (size_t)rbase * g.ldr + col;
+          const float* src = g.res + (size_t)rbase * ldr + col;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) rs[i] = (rbase + i < g.M) ? __ldg(src + (size_t)i * g.ldr) : 0.f;
+          for (int i = 0; i < 32; ++i) rs[i] = (rbase + i < g.M) ? __ldg(src + (size_t)i * ldr) : 0.f;
         };
         if (EPI == EPI_RES_BN) load_res_sw(r_first);            // independent of the MMAs: issued before the accumulator is ready
         mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
@@ -522,11 +529,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           const int rbase = mt * BM + rc;
           float* dst = Cb + (size_t)rbase * ldc + col;
+          if (rbase + 32 <= g.M) {          // every row tile but the last: no per-row predicates
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = r[i];
-            if (EPI == EPI_BIAS_RELU) v = fmaxf(v + bias, 0.f);
-            if (rbase + i < g.M) dst[(size_t)i * ldc] = v;
+            for (int i = 0; i < 32; ++i) {
+              float v = r[i];
+              if (EPI == EPI_BIAS_RELU) v = fmaxf(v + bias, 0.f);
+              dst[(size_t)i * ldc] = v;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float v = r[i];
+              if (EPI == EPI_BIAS_RELU) v = fmaxf(v + bias, 0.f);
+              if (rbase + i < g.M) dst[(size_t)i * ldc] = v;
+            }
           }
         }
         if (warp == 6 && lane == 0) TR(7, tile);
@@ -538,9 +554,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // MMAs, so its (coalesced) loads are issued BEFORE waiting for the accumulator and one chunk ahead after that.
       float rr[32];
       auto load_res = [&](int c0, float (&dst)[32]) {
-        const float* src = g.res + (size_t)row0 * g.ldr + n0 + c0 + lane;
+        const float* src = g.res + (size_t)row0 * ldr + n0 + c0 + lane;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dst[i] = (row0 + i < g.M) ? __ldg(src + (size_t)i * g.ldr) : 0.f;
+        for (int i = 0; i < 32; ++i) dst[i] = (row0 + i < g.M) ? __ldg(src + (size_t)i * ldr) : 0.f;
       };
       // fragment domain: thread (g8, t4) owns rows row0 + 8 rq + g8 (rq = 0..3) and column pairs 8 k + 2 t4 (k = 0..3)
       const int g8 = lane >> 2, t4 = lane & 3;
@@ -549,7 +565,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int rq = 0; rq < 4; ++rq) {
           const int row = row0 + rq * 8 + g8;
-          const float* src = g.res + (size_t)row * g.ldr + n0 + c0 + 2 * t4;
+          const float* src = g.res + (size_t)row * ldr + n0 + c0 + 2 * t4;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             fres[rq * 4 + k] = row < g.M ? __ldg(reinterpret_cast<const float2*>(src + 8 * k)) : make_float2(0.f, 0.f);
@@ -662,7 +678,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 bb = *reinterpret_cast<const float4*>(s_vec + c0 + v4 * 4);
                 v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
               }
-              const float4 rr = __ldg(reinterpret_cast<const float4*>(g.res + (size_t)row * g.ldr + col));
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(g.res + (size_t)row * ldr + col));
               const float4 sc = *reinterpret_cast<const float4*>(s_vec + BN + c0 + v4 * 4);
               const float4 sh = *reinterpret_cast<const float4*>(s_vec + 2 * BN + c0 + v4 * 4);
               v.x = fmaf(rr.x + v.x, sc.x, sh.x); v.y = fmaf(rr.y + v.y, sc.y, sh.y);
@@ -787,13 +803,31 @@ static int launch_cfg(const GemmArgs& g, cudaStream_t st) {
   if (rc) return rc;
   rc = make_map(&tmW, g.Wt, (uint64_t)g.Nc, (uint64_t)g.K, (uint64_t)g.K);
   if (rc) return rc;
-  auto kern = gemm_tc_kernel<EPI, WRES>;
-  AGH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   const int n_tiles = g.Nc / BN, m_tiles = ceil_div(g.M, BM);
   int per_slab = sm_count() / n_tiles;                 // persistent: one CTA per SM, CTAs of a slab stride over the row tiles
   if (per_slab < 1) per_slab = 1;
   if (per_slab > m_tiles) per_slab = m_tiles;
   dim3 grid(per_slab, n_tiles);
+  if (EPI == EPI_RES_BN && (g.ldc != BN || g.ldr != BN)) {
+    set_error("gemm_tc: the residual epilogue expects [M][128] output and residual (ldc=%d ldr=%d)", g.ldc, g.ldr);
+    return AGH_E_UNSUPPORTED;
+  }
+  constexpr bool SLAB_OK = WRES && (EPI == EPI_PLAIN || EPI == EPI_BIAS_RELU);
+  if (g.c_slab && !SLAB_OK) {
+    set_error("gemm_tc: slab-major output is built for the K = 128 plain / bias+ReLU kernels only");
+    return AGH_E_UNSUPPORTED;
+  }
+  if constexpr (SLAB_OK) {
+    if (g.c_slab) {
+      auto kern = gemm_tc_kernel<EPI, WRES, true>;
+      AGH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      kern<<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmW, g);
+      AGH_LAUNCH_CHECK();
+      return AGH_OK;
+    }
+  }
+  auto kern = gemm_tc_kernel<EPI, WRES, false>;
+  AGH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   kern<<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmW, g);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
