@@ -1,19 +1,25 @@
 // Tensor-core GEMM for the encoder / precompute contractions:  C[M,Nc] = epi(A[M,K] @ W[Nc,K]^T), fp32 in,
-// fp32 out, computed on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) with the 3xTF32 split
-//      a = a_hi + a_lo,  w = w_hi + w_lo   (hi = rn_tf32(x), lo = rn_tf32(x - hi))
+// fp32 out, computed on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) with a two-term operand split
+//      a = a_hi + a_lo,  w = w_hi + w_lo
 //      a.w ~= a_hi.w_hi + a_hi.w_lo + a_lo.w_hi            (dropped term ~2^-22 relative)
-// so the result keeps fp32-level accuracy (the 1e-4 log-prob tolerance rules out plain tf32 / bf16).
+// so the result keeps fp32-level accuracy (the 1e-4 log-prob tolerance rules out plain tf32 / bf16 / fp16 operands).
+// Shipped form (AGH_TC_F16 = 1): hi = rn_f16(x), lo' = rn_f16((x - hi) * 2048), kind::f16 MMAs of K = 16, the cross
+// accumulator scaled by 2^-11 in the epilogue; AGH_TC_F16 = 0: hi = rn_tf32(x), lo = rn_tf32(x - hi), kind::tf32 MMAs
+// of K = 8 (the form the scheme was first validated with).  Stage sizes below are those of the FP16 form.
 //
 // Persistent, warp-specialised kernel: each CTA owns one 128-column slab of W and loops over 128-row tiles of A.
-//   warp 0      : TMA producer  - cp.async.bulk.tensor (SWIZZLE_128B) of [128 x 32] fp32 blocks into a 3-stage ring
-//   warp 1      : MMA issuer    - one elected lane issues 3 tcgen05.mma.kind::tf32 per K=8 step; tcgen05.commit
+//   warp 0      : TMA producer  - cp.async.bulk.tensor (SWIZZLE_128B) boxes of [128 x 32] fp32, two per operand and
+//                                 stage (K = 64), into a ring of 4 (K = 128 kernels) or 3 (K = 512) stages
+//   warp 1      : MMA issuer    - one elected lane issues 3 tcgen05.mma per K=16 step; tcgen05.commit
 //                                 releases the smem stage / hands the TMEM accumulator to the epilogue
-//   warps 2..5  : splitters     - hi/lo split of the landed fp32 blocks in shared memory (element-wise, so the TMA
-//                                 swizzle is irrelevant), fence.proxy.async
-//   warps 6..13 : epilogue      - tcgen05.ld -> bias / ReLU / residual + BatchNorm / key scatter -> HBM, overlapped
+//   warps 2..5  : splitters     - one thread per row rewrites the two landed fp32 boxes of a stage IN PLACE as the
+//                                 K-major SWIZZLE_128B fp16 blocks of hi and lo' ([128 x 64 halfs] each), fence.proxy.async
+//   warps 6..13 : epilogue      - tcgen05.ld -> bias / ReLU / residual + BatchNorm -> HBM, overlapped
 //                                 with the next tile's main loop through a double-buffered TMEM accumulator
-// K = 128 (QKV, out-projection, FF1, decoder projection): the W slab (hi + lo, 128 KB) is loaded and split ONCE
+// K = 128 (QKV, out-projection, FF1, decoder projection): the W slab (hi + lo', 64 KB) is loaded and split ONCE
 // per CTA and stays resident; only A streams.  K = 512 (FF2): W blocks stream with A.
+// Wide outputs (QKV, FF1, decoder projection) are written slab-major -- one [M][128] matrix per 128-column slab, so a
+// CTA's tile is a contiguous 64 KB block -- and FF2 reads its A operand from that form (GemmArgs::c_slab / a_slab).
 //
 // The tensor core adds into its fp32 accumulator with truncation, so the error grows with the number of sequential
 // accumulations: the small cross terms go to their own accumulator (and, for K = 512, the hi.hi terms are spread

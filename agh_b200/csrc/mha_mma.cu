@@ -1,20 +1,20 @@
-// Encoder self-attention on the warp-level tensor-core path (mma.sync m16n8k8, 3xTF32): graph_encoder.py:83-104.
+// Encoder self-attention on the warp-level tensor-core path (mma.sync): graph_encoder.py:83-104.
 //
 // The attention of one (instance, head) is two tiny GEMMs, S = Q K^T ([n,16] x [16,n]) and O = softmax(S) V
 // ([n,n] x [n,16]) with n = N+1 <= 301 -- far too small for a tcgen05 tile pipeline, but exactly the shape of
-// mma.sync fragments held in registers.  One warp owns 16 query rows; it walks the keys in chunks of CH fragments
+// mma.sync fragments held in registers.  One warp owns 16 query rows; it walks the keys in chunks of CH score tiles
 // of 8 keys with a base-2 online softmax between the two products, so the [n,n] score matrix lives only in
-// registers.  fp32 accuracy comes from the same 3xTF32 split the tcgen05 GEMM uses: x = hi + lo with hi, lo
-// representable in TF32, and  a*b ~= hi_a*hi_b + (lo_a*hi_b + hi_a*lo_b).  For S (a 16-term sum) the cross products
-// are issued first so the small terms enter the accumulator before the large ones; for O (a sum over all keys) they
-// have their own accumulator so that they are not absorbed by the growing partial sums.
+// registers.  fp32 accuracy comes from the same two-term operand split the tcgen05 GEMM uses,
+// a*b ~= hi_a*hi_b + (lo_a*hi_b + hi_a*lo_b), with the cross products in their own accumulators so that they are not
+// absorbed by the growing partial sums.  Shipped form (AGH_MHA_F16 = 1): fp16 (hi, lo' = (x - hi) 2^11) operands on
+// m16n8k16 -- one instruction spans the head dimension of S and 16 keys of P V; AGH_MHA_F16 = 0: TF32 (hi, lo) on m16n8k8.
 //
-// One CTA walks the 8 heads of one instance.  K_h and V_h are rewritten in shared memory as TF32 (hi, lo) values in
-// fragment order: the two B-fragment registers of every mma are adjacent (K: columns t and t+4 of one key; V: keys
-// 2t and 2t+1 of one column), so each fragment is ONE LDS.64 straight into the register pair the instruction needs;
-// row strides of 20 and 36 pairs keep those loads bank-conflict free.  The P fragments of the second product are the
-// score fragments themselves: a thread's score columns (2t, 2t+1) are fed as A-columns (t, t+4) and the V pairs
-// follow the same key order, so no shuffle is needed between the two products.
+// One CTA walks the 8 heads of one instance.  K_h and V_h are rewritten in shared memory as (hi, lo') words in
+// fragment order: the two B-fragment registers of every mma are adjacent (FP16 form -- K: dims {2t,2t+1 | 2t+8,2t+9} of
+// one key, 96-byte key stride; V: keys {2t,2t+1 | 2t+8,2t+9} of one dim, 1 KB per 16 keys), so each fragment is ONE
+// conflict-free LDS.64 straight into the register pair the instruction needs.  The P fragments of the second product
+// are the score fragments themselves (FP16 form: a pair of score tiles is the m16k16 A fragment as it stands), so no
+// shuffle is needed between the two products.
 //
 // Two kernels share that inner routine:
 //  * mha_ws_kernel (default when it fits): warp-specialised.  One producer warp streams the raw K_h|V_h rows of the
