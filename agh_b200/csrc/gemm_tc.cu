@@ -12,9 +12,10 @@
 //                                 stage (K = 64), into a ring of 4 (K = 128 kernels) or 3 (K = 512) stages
 //   warp 1      : MMA issuer    - one elected lane issues 3 tcgen05.mma per K=16 step; tcgen05.commit
 //                                 releases the smem stage / hands the TMEM accumulator to the epilogue
-//   warps 2..5  : splitters     - one thread per row rewrites the two landed fp32 boxes of a stage IN PLACE as the
-//                                 K-major SWIZZLE_128B fp16 blocks of hi and lo' ([128 x 64 halfs] each), fence.proxy.async
-//   warps 6..13 : epilogue      - tcgen05.ld -> bias / ReLU / residual + BatchNorm -> HBM, overlapped
+//   warps 2..9  : splitters     - two threads per row (one per raw box) rewrite the two landed fp32 boxes of a stage IN
+//                                 PLACE as the K-major SWIZZLE_128B fp16 blocks of hi and lo' ([128 x 64 halfs] each),
+//                                 fence.proxy.async  (TF32 build: warps 2..5, epilogue 6..13)
+//   warps 10..17: epilogue      - tcgen05.ld -> bias / ReLU / residual + BatchNorm -> HBM, overlapped
 //                                 with the next tile's main loop through a double-buffered TMEM accumulator
 // K = 128 (QKV, out-projection, FF1, decoder projection): the W slab (hi + lo', 64 KB) is loaded and split ONCE
 // per CTA and stays resident; only A streams.  K = 512 (FF2): W blocks stream with A.
@@ -54,7 +55,12 @@ constexpr int KST = F16 ? 2 * BK : BK;                 // K extent of one pipeli
 constexpr int STAGES_WRES = F16 ? 4 : 3, STAGES_STREAM = 3;
 constexpr float CROSS_SCALE = F16 ? 1.0f / 2048.0f : 1.0f;
 constexpr int EPI_WARPS = 8;                          // two per TMEM lane quarter, each takes half of the column chunks
-constexpr int NTHREADS = 192 + 32 * EPI_WARPS;
+// Splitter warps: the per-role timeline of the FP16 build (profiles/r1h_fp16_split_notes.md, r1j) shows the K = 128 shapes
+// bound by the splitters (1.1 us per K = 64 stage with four warps against a 1.75 us epilogue per two-stage tile), so
+// the FP16 form runs eight: two threads per row, one per raw box.
+constexpr int SPLIT_WARPS = F16 ? 8 : 4;
+constexpr int FIRST_EPI = 2 + SPLIT_WARPS;            // warp index of the first epilogue warp (a multiple of 2: quarters by warp % 4)
+constexpr int NTHREADS = 32 * (2 + SPLIT_WARPS + EPI_WARPS);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -212,6 +218,38 @@ __device__ __forceinline__ void split_f16_row(unsigned char* r0, unsigned char* 
   }
 }
 
+// The same split with TWO threads per row (256 splitter threads): lanes l and l + 16 of a warp share row 16 w + (l & 15);
+// the lower one reads the raw box of k = 0..31 and produces fp16 chunks 0..3 of hi and lo', the upper one k = 32..63 and
+// chunks 4..7.  Both destinations of a row overlap both sources, hence the __syncwarp between the reads and the writes.
+__device__ __forceinline__ void split_f16_half(unsigned char* r0, unsigned char* r1, int t) {
+  const int row = (t >> 5) * 16 + (t & 15), half = (t >> 4) & 1, x = row & 7;
+  const unsigned char* src = (half ? r1 : r0) + row * 128;
+  float4 v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + ((c ^ x) << 4));
+  __syncwarp();
+  unsigned char* p0 = r0 + row * 128;
+  unsigned char* p1 = r1 + row * 128;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = half * 4 + jj;
+    const float f[8] = {v[2 * jj].x, v[2 * jj].y, v[2 * jj].z, v[2 * jj].w, v[2 * jj + 1].x, v[2 * jj + 1].y, v[2 * jj + 1].z, v[2 * jj + 1].w};
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint32_t h2;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(f[2 * e + 1]), "f"(f[2 * e]));
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+      const float d0 = (f[2 * e] - hf.x) * 2048.0f, d1 = (f[2 * e + 1] - hf.y) * 2048.0f;
+      uint32_t l2;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
+      hw[e] = h2; lw[e] = l2;
+    }
+    *reinterpret_cast<uint4*>(p0 + ((j ^ x) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(p1 + ((j ^ x) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
 // WRES = true : K == 128, W slab resident (hi 64 KB + lo 64 KB), stage = A hi|lo (32 KB), 2 TMEM buffers of {main, cross}
 // WRES = false: K % 32 == 0, stage = A hi|lo + W hi|lo (64 KB), 1 TMEM buffer of {3 main, cross}
 template <bool WRES>
@@ -321,7 +359,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_raw(s), 1);
-      mbar_init(bar_split(s), 128);
+      mbar_init(bar_split(s), SPLIT_WARPS * 32);
       mbar_init(bar_empty(s), 1);
     }
     for (int b = 0; b < C::NBUF; ++b) {
@@ -329,7 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(bar_tempty(b), EPI_WARPS);
     }
     mbar_init(bar_wraw, 1);
-    mbar_init(bar_wsplit, 128);
+    mbar_init(bar_wsplit, SPLIT_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation (whole warp): all 512 columns, one CTA per SM
@@ -426,14 +464,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
-    // ================= splitters (warps 2..5, 128 threads) =================
+  } else if (warp < FIRST_EPI) {
+    // ================= splitters (warps 2 .. FIRST_EPI-1) =================
     const int t = threadIdx.x - 64;
     if (WRES) {
       mbar_wait(bar_wraw, 0);
       if (F16) {
-        split_f16_row(wres, wres + BLK, t);
-        split_f16_row(wres + 2 * BLK, wres + 3 * BLK, t);
+        split_f16_half(wres, wres + BLK, t);
+        split_f16_half(wres + 2 * BLK, wres + 3 * BLK, t);
       } else {
         split_block(wres, wres + 4 * BLK, 4 * BLK / 16, t);
       }
@@ -448,8 +486,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (t == 0) TR(1, it);
         unsigned char* st = ring + s * C::STAGE_BYTES;
         if (F16) {
-          split_f16_row(st, st + BLK, t);
-          if (!WRES) split_f16_row(st + 2 * BLK, st + 3 * BLK, t);
+          split_f16_half(st, st + BLK, t);
+          if (!WRES) split_f16_half(st + 2 * BLK, st + 3 * BLK, t);
         } else {
           split_block(st, st + BLK, BLK / 16, t);
           if (!WRES) split_block(st + 2 * BLK, st + 3 * BLK, BLK / 16, t);
@@ -460,10 +498,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ================= epilogue (warps 6..13): TMEM lane quarter = warp % 4; the two warps of a quarter split the
+    // ================= epilogue (warps FIRST_EPI ..): TMEM lane quarter = warp % 4; the two warps of a quarter split the
     // four 32-column chunks of the tile between them =================
     const int q = warp & 3;
-    const int chalf = (warp - 6) >> 2;                          // 0: chunks 0,1   1: chunks 2,3
+    const int chalf = (warp - FIRST_EPI) >> 2;                          // 0: chunks 0,1   1: chunks 2,3
     // EPI_DEC: the four 128-column slabs are four plain [M][128] matrices -- K', V, LK' (keys[0..2]) and P_sc -- so the
     // epilogue is the plain one with a per-slab base (shifted by n0 because `col` below is the GEMM's global column)
     float* Cb = g.C;
@@ -499,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         if (EPI == EPI_RES_BN) load_res_sw(r_first);            // independent of the MMAs: issued before the accumulator is ready
         mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
-        if (warp == 6 && lane == 0) TR(5, tile);
+        if (warp == FIRST_EPI && lane == 0) TR(5, tile);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t_acc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -523,7 +561,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty(ab));
-            if (warp == 6 && lane == 0) TR(6, tile);
+            if (warp == FIRST_EPI && lane == 0) TR(6, tile);
           }
 #ifdef AGH_TC_SKIP_EPILOGUE
           if (r[0] != 12345.678f) continue;
@@ -551,7 +589,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        if (warp == 6 && lane == 0) TR(7, tile);
+        if (warp == FIRST_EPI && lane == 0) TR(7, tile);
         continue;
       }
       const int row0 = mt * BM + q * 32;
@@ -582,7 +620,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else if (epi_transposed(EPI)) load_res(c_first, rr);
       }
       mbar_wait(bar_tfull(ab), (tile / C::NBUF) & 1);
-      if (warp == 6 && lane == 0) TR(5, tile);
+      if (warp == FIRST_EPI && lane == 0) TR(5, tile);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t t_acc = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
       if (epi_frag(EPI)) {
@@ -609,7 +647,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty(ab));
-            if (warp == 6 && lane == 0) TR(6, tile);
+            if (warp == FIRST_EPI && lane == 0) TR(6, tile);
           }
 #ifdef AGH_TC_SKIP_EPILOGUE
           if (r[0] != 12345.678f) continue;
@@ -639,7 +677,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (EPI == EPI_RES_BN && c0 < c_last) load_res_frag(c0 + 32);      // next chunk's residual: in flight during its TMEM reads
         }
-        if (warp == 6 && lane == 0) TR(7, tile);
+        if (warp == FIRST_EPI && lane == 0) TR(7, tile);
         continue;
       }
 #pragma unroll 1
@@ -663,7 +701,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty(ab));
-          if (warp == 6 && lane == 0) TR(6, tile);
+          if (warp == FIRST_EPI && lane == 0) TR(6, tile);
         }
 #ifdef AGH_TC_SKIP_EPILOGUE      // measurement only: main-loop-bound time (results are NOT written)
         if (r[0] != 12345.678f) continue;
@@ -725,7 +763,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (row < g.M) Cb[(size_t)row * ldc + col] = v;
         }
       }
-      if (warp == 6 && lane == 0) TR(7, tile);
+      if (warp == FIRST_EPI && lane == 0) TR(7, tile);
     }
   }
 

@@ -28,7 +28,11 @@ def main():
     for l in sorted(tr):
         r = tr[l]
         epi, wres = meta[l]
-        nkb = 4 if wres else 16
+        # k-blocks per tile and ring depth: FP16 build (default) K = 64 per stage, 4 / 3 stages; --tf32: K = 32, 3 stages
+        tf32 = '--tf32' in sys.argv
+        nkb = (4 if wres else 16) if tf32 else (2 if wres else 8)
+        depth = 3 if (tf32 or not wres) else 4
+        kst = 32 if tf32 else 64
         n = min(len(r[0]), len(r[1]), len(r[2]), len(r[3]), len(r[4]))
         ks = [i for i in range(8, n)]
         if not ks:
@@ -39,12 +43,12 @@ def main():
             return sum(v) / len(v)
 
         per_kb = (r[4][ks[-1]] - r[4][ks[0]]) / (len(ks) - 1)
-        print('launch %d  %s  K=%d: %.0f ns per k-block = %.2f us per tile in steady state' % (l, EPI[epi], 32 * nkb, per_kb, per_kb * nkb / 1e3))
+        print('launch %d  %s  K=%d: %.0f ns per k-block = %.2f us per tile in steady state' % (l, EPI[epi], kst * nkb, per_kb, per_kb * nkb / 1e3))
         print('   TMA issue -> raw landed        %6.0f ns' % mean(lambda i: r[1][i] - r[0][i]))
         print('   raw landed -> split done       %6.0f ns' % mean(lambda i: r[2][i] - r[1][i]))
         print('   split done -> MMA sees it      %6.0f ns' % mean(lambda i: r[3][i] - r[2][i]))
         print('   MMA issue + commit             %6.0f ns' % mean(lambda i: r[4][i] - r[3][i]))
-        print('   commit -> stage refilled (TMA issue of k-block i+3)  %6.0f ns' % mean(lambda i: r[0][i + 3] - r[4][i] if i + 3 in r[0] else 0))
+        print('   commit -> stage refilled (TMA issue of k-block i+depth)  %6.0f ns' % mean(lambda i: r[0][i + depth] - r[4][i] if i + depth in r[0] else 0))
         tiles = [t for t in range(2, min(len(r[5]), len(r[6]), len(r[7])))]
         if tiles:
             def tmean(f):
