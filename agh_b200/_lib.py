@@ -21,7 +21,7 @@ NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,c
               '-std=c++17']
 
 AGH_GREEDY, AGH_SAMPLING, AGH_REPLAY = 0, 1, 2
-AGH_TOUR_INVALID, AGH_CAPACITY_EXCEEDED, AGH_TW_VIOLATED = 1, 2, 4
+AGH_TOUR_INVALID, AGH_CAPACITY_EXCEEDED, AGH_TW_VIOLATED, AGH_DECODE_STUCK = 1, 2, 4, 8
 KEY_STRIDE = 128
 D = 128
 
@@ -67,8 +67,9 @@ class DecodeArgs(C.Structure):
         ('demand', C.c_void_p), ('tw_left', C.c_void_p), ('tw_right', C.c_void_p), ('duration', C.c_void_p),
         ('distance', C.c_void_p), ('wblob', C.c_void_p),
         ('key_mod', C.c_int), ('smem_mats', C.c_int), ('mode', C.c_int), ('temp', C.c_float), ('seed', C.c_uint64), ('id_offset', C.c_int64),
-        ('actions', C.c_void_p), ('replay_steps', C.c_int), ('inject_logp', C.c_void_p), ('t_stride', C.c_int),
-        ('pi', C.c_void_p), ('steps', C.c_void_p), ('ll', C.c_void_p), ('cost', C.c_void_p), ('serve', C.c_void_p),
+        ('actions', C.c_void_p), ('replay_steps', C.c_int), ('inject_logp', C.c_void_p), ('inject_z', C.c_void_p),
+        ('t_stride', C.c_int),
+        ('pi', C.c_void_p), ('steps', C.c_void_p), ('status', C.c_void_p), ('ll', C.c_void_p), ('cost', C.c_void_p), ('serve', C.c_void_p),
         ('logp_sel', C.c_void_p), ('logp_full', C.c_void_p), ('mask_dump', C.c_void_p), ('used_dump', C.c_void_p),
         ('cft_dump', C.c_void_p), ('B', C.c_int), ('N', C.c_int),
     ]
@@ -144,4 +145,10 @@ def ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
 
 
 def stream_ptr(device=None) -> int:
+    """Current stream of `device`.  The C ABI launches on the CURRENT device, so the tensors' device must be it."""
+    if device is not None:
+        idx = torch.device(device).index
+        if idx is not None and idx != torch.cuda.current_device():
+            raise AghError('tensors live on cuda:%d but the current device is cuda:%d: call torch.cuda.set_device(%d) '
+                           '(or wrap the call in torch.cuda.device) first' % (idx, torch.cuda.current_device(), idx))
     return torch.cuda.current_stream(device).cuda_stream

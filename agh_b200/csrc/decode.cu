@@ -91,6 +91,20 @@ __device__ __forceinline__ uint32_t pick_word(const uint32_t (&w)[NPL], int idx)
   return r;
 }
 
+// order-preserving float <-> int map (its own inverse): integer REDUX / compares on float scores
+__device__ __forceinline__ int fkey(float x) {
+  int k = __float_as_int(x);
+  return k ^ ((k >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
+// Greedy selection is argmax_j exp(log_p_j) with the first index winning ties (attention_model.py:333,377), and
+// log_p_j = (z_j - max z) - log(sum) is rounded on the grid of log(sum) (at most 2^-21 for n <= 301), which collapses
+// logits closer than that to the maximum into a tie.  Logits further than NEAR_TIE below the maximum can never tie with
+// it (>= 4 grid steps in every binade, and exp keeps them apart), so the fast path selects on z itself and only steps
+// with a second logit inside the window re-decide with the reference's formula (rare: ~1e-5 of the steps).
+constexpr float NEAR_TIE = 2e-6f;
+
 // Residency of the per-instance matrices.  K' always lives in REGISTERS (lane l of warp h holds the 16
 // features of head h for its nodes l, l+32, ...: 16*NPL registers, the exact operand layout of the
 // compatibility dot products).  V / LK' / P_sc live in shared memory when the bit is set, else they are
@@ -279,6 +293,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   // normal, hence temp >= 0.25); colder temperatures take the exact max-merging path
   const bool fixed_shift = a.temp >= 0.25f;
   const float shift = __fdiv_rn(10.0f, a.temp);
+  const bool tie_check = a.mode == AGH_GREEDY && a.inject_logp == nullptr;     // production greedy selection
 
   // (1) distance from the current location to the node(s) this thread masks, and this thread's component of the
   //     current node's P_sc row when that table is not in shared memory: both come through L2, so they are requested
@@ -289,7 +304,11 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   float pv_r = 0.f;
   if (!(RES & RES_P) && qi >= 0) pv_r = __ldg(Pm + qi);
 
-  while (replay ? (t < a.replay_steps) : (nvis < n)) {
+  // the step budget bounds the loop: an instance whose unvisited nodes are all infeasible (demand > capacity, a time
+  // window that cannot be met from the depot) would select the depot forever -- the reference spins in its Python loop;
+  // here the instance stops with AGH_DECODE_STUCK in its status word
+  const int tmax = replay ? a.replay_steps : a.t_stride;
+  while (t < tmax && (replay || nvis < n)) {
     float* dc = s_dcur + (t & 1) * NPAD;
     // like dc, double-buffered by step parity: a fast warp's writes of step t+1 must not overtake a slow warp's
     // reads of step t (no barrier separates a step's selection phase from the next step's mask phase)
@@ -484,7 +503,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       //     swizzled 128-byte group (conflict-free) and the matching chunks of o are a broadcast across the 4 nodes.
       const int ns = lane >> 3, fg = lane & 7;
       // selection score as an order-preserving integer key, so the arg-max is two warp REDUX operations
-      int best_key = (int)0x80000000;
+      int best_key = (int)0x80000000, second_key = (int)0x80000000;
       int best_j = 0x7fffffff;
       float wm = shift, ws = 0.f;
       for (int c0 = warp * 4; c0 < nfeas; c0 += 32) {
@@ -504,6 +523,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         u += __shfl_xor_sync(0xffffffffu, u, 4);
         if (valid && fg == 0) {
           float z = 10.0f * tanhf(u);                               // attention_model.py:580
+          if (a.inject_z != nullptr) z = __ldg(a.inject_z + (trow + t) * n + j);
           if (!unit_temp) z = __fdiv_rn(z, a.temp);                 // :447
           s_z[j] = z;
           float sc = z;
@@ -513,9 +533,10 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
             sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
           }
           if (fixed_shift) ws += expf(z - shift);
-          int key = __float_as_int(sc);
-          key ^= (key >> 31) & 0x7fffffff;                          // monotone float -> int map
-          if (key > best_key) { best_key = key; best_j = j; }       // strict: the list is in index order, first index wins ties
+          const int key = fkey(sc);
+          // strict: the list is in index order, first index wins ties; the runner-up feeds the near-tie test
+          if (key > best_key) { second_key = best_key; best_key = key; best_j = j; }
+          else if (key > second_key) second_key = key;
         }
       }
       if (!fixed_shift) {                                           // cold temperatures: exact max-merging log-sum-exp
@@ -532,7 +553,12 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       for (int off = 16; off >= 1; off >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, off);
       {
         const int kmax = __reduce_max_sync(0xffffffffu, best_key);
-        const int jmin = __reduce_min_sync(0xffffffffu, best_key == kmax ? best_j : 0x7fffffff);
+        int jmin = __reduce_min_sync(0xffffffffu, best_key == kmax ? best_j : 0x7fffffff);
+        if (tie_check) {      // does this warp hold a second logit within NEAR_TIE of its best one?
+          const int kthr = fkey(fkey_inv(kmax) - NEAR_TIE);
+          const bool mine = best_key == kmax && best_j == jmin;
+          if (__any_sync(0xffffffffu, (!mine && best_key >= kthr) || second_key >= kthr)) jmin |= 0x10000;
+        }
         if (lane == 0)
           *reinterpret_cast<float4*>(s_red + warp * 4) = make_float4(ws, __int_as_float(kmax), __int_as_float(jmin), wm);
       }
@@ -542,7 +568,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       constexpr int NPASS = (NPL * 32 + 127) / 128;
       float zp[NPASS];
       // selection score as an order-preserving integer key, so the arg-max is two warp REDUX operations
-      int best_key = (int)0x80000000;
+      int best_key = (int)0x80000000, second_key = (int)0x80000000;
       int best_j = 0x7fffffff;
   #pragma unroll
       for (int ps = 0; ps < NPASS; ++ps) {
@@ -566,6 +592,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         float z = -CUDART_INF_F;
         if (!mj) {
           z = 10.0f * tanhf(u);                                   // attention_model.py:580
+          if (a.inject_z != nullptr) z = __ldg(a.inject_z + (trow + t) * n + j);
           if (!unit_temp) z = __fdiv_rn(z, a.temp);               // :447
         }
         if (half == 0 && j < n) s_z[j] = z;
@@ -576,9 +603,11 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
           sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
         }
         zp[ps] = (half == 0) ? z : -CUDART_INF_F;
-        int key = __float_as_int(sc);
-        key ^= (key >> 31) & 0x7fffffff;                          // monotone float -> int map
-        if (half == 0 && key > best_key) { best_key = key; best_j = j; }     // strict: first index wins ties
+        const int key = fkey(sc);
+        if (half == 0) {                                          // strict: first index wins ties
+          if (key > best_key) { second_key = best_key; best_key = key; best_j = j; }
+          else if (key > second_key) second_key = key;
+        }
       }
       float wm = shift, ws = 0.f;
       if (!fixed_shift) {
@@ -594,7 +623,12 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       for (int off = 16; off >= 1; off >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, off);
       {
         const int kmax = __reduce_max_sync(0xffffffffu, best_key);
-        const int jmin = __reduce_min_sync(0xffffffffu, best_key == kmax ? best_j : 0x7fffffff);
+        int jmin = __reduce_min_sync(0xffffffffu, best_key == kmax ? best_j : 0x7fffffff);
+        if (tie_check) {      // does this warp hold a second logit within NEAR_TIE of its best one?
+          const int kthr = fkey(fkey_inv(kmax) - NEAR_TIE);
+          const bool mine = best_key == kmax && best_j == jmin;
+          if (__any_sync(0xffffffffu, (!mine && best_key >= kthr) || second_key >= kthr)) jmin |= 0x10000;
+        }
         if (lane == 0)
           *reinterpret_cast<float4*>(s_red + warp * 4) = make_float4(ws, __int_as_float(kmax), __int_as_float(jmin), wm);
       }
@@ -610,7 +644,35 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       if (lane < 8) pr = *reinterpret_cast<const float4*>(s_red + lane * 4);
       const int key = __float_as_int(pr.y);
       const int kmax = __reduce_max_sync(0xffffffffu, key);
-      sel = __reduce_min_sync(0xffffffffu, key == kmax ? __float_as_int(pr.z) : 0x7fffffff);
+      const int jw = __float_as_int(pr.z) & 0xffff;
+      sel = __reduce_min_sync(0xffffffffu, key == kmax ? jw : 0x7fffffff);
+      if (tie_check) {
+        // another warp's best logit, or a second one of the winning warp, within NEAR_TIE of the maximum
+        const float zmax = fkey_inv(kmax);
+        const int kthr = fkey(zmax - NEAR_TIE);
+        if (__any_sync(0xffffffffu, lane < 8 && key >= kthr && (jw != sel || (__float_as_int(pr.z) & 0x10000)))) {
+          // re-decide with the reference's arithmetic: log_p = (z - max) - log(sum exp(z - max)), p = exp(log_p),
+          // first index of the maximum (attention_model.py:446-447,333,377).  Every warp computes the same values.
+          float ssum = 0.f;
+          for (int j = lane; j < n; j += 32) {
+            const float z = s_z[j];
+            ssum += (z == -CUDART_INF_F) ? 0.f : expf(z - zmax);
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, off);
+          const float lse = logf(ssum);
+          int pk = (int)0x80000000, pj = 0x7fffffff;
+          for (int j = lane; j < n; j += 32) {
+            const float z = s_z[j];
+            if (z >= zmax - NEAR_TIE) {
+              const int k2 = __float_as_int(expf((z - zmax) - lse));      // p > 0: its bits order like the value
+              if (k2 > pk) { pk = k2; pj = j; }
+            }
+          }
+          const int pmax = __reduce_max_sync(0xffffffffu, pk);
+          sel = __reduce_min_sync(0xffffffffu, pk == pmax ? pj : 0x7fffffff);
+        }
+      }
       float part = pr.x;
       if (!fixed_shift) {
         float wmax = pr.w;
@@ -668,6 +730,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     a.cost[b] = __fadd_rn(len, back);
     a.ll[b] = ll;
     a.steps[b] = t;
+    if (a.status != nullptr) a.status[b] = (!replay && nvis < n) ? AGH_DECODE_STUCK : 0;
   }
   for (int j = tid; j < n; j += 256) a.serve[(size_t)b * n + j] = s_serve[j];
   for (int k = t + tid; k < a.t_stride; k += 256) {
@@ -729,7 +792,7 @@ extern "C" int agh_decode(const agh_decode_args* args, void* stream) {
   AGH_CHECK_ARG(a.distance && a.wblob && a.pi && a.steps && a.ll && a.cost && a.serve);
   AGH_CHECK_ARG(a.mode == AGH_GREEDY || a.mode == AGH_SAMPLING || a.mode == AGH_REPLAY);
   AGH_CHECK_ARG(a.mode != AGH_REPLAY || (a.actions != nullptr && a.replay_steps >= 0 && a.replay_steps <= a.t_stride));
-  AGH_CHECK_ARG(a.t_stride >= 2 * a.N - 1 && a.t_stride >= 1);
+  AGH_CHECK_ARG(a.t_stride >= 2 * a.N - 1 && a.t_stride >= 2);      // N = 1 takes two steps: the node, then the depot
   AGH_CHECK_ARG(a.temp > 0.f);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int npl = ceil_div(a.N + 1, 32);

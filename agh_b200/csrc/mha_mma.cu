@@ -574,11 +574,9 @@ template <int CH, int MAXT, int MINB>
 int launch_uniform(const float* qkv, int rs, size_t ps, int B, int n, int hpc, int mt, float* heads, cudaStream_t st) {
   const int npad = ceil_div(n, 8 * CH) * 8 * CH;
   const size_t smem = (size_t)hpc * lane_bytes(npad);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  // the opt-in is a per-device attribute: set it on every launch (a process may drive several GPUs)
+  if (smem > 48 * 1024)
     AGH_CUDA(cudaFuncSetAttribute(mha_mma_kernel<CH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   mha_mma_kernel<CH, MAXT, MINB><<<B, hpc * mt * 32, smem, st>>>(qkv, rs, ps, n, hpc, mt, heads);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
@@ -588,11 +586,9 @@ template <int CH, int MAXT, int MINB>
 int launch_ws(const float* qkv, int rs, size_t ps, int B, int n, int mt, float* heads, cudaStream_t st) {
   const int npad = ceil_div(n, 8 * CH) * 8 * CH;
   const size_t smem = ws_smem_bytes(n, npad);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  // the opt-in is a per-device attribute: set it on every launch (a process may drive several GPUs)
+  if (smem > 48 * 1024)
     AGH_CUDA(cudaFuncSetAttribute(mha_ws_kernel<CH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   mha_ws_kernel<CH, MAXT, MINB><<<B, (mt + 1) * 32, smem, st>>>(qkv, rs, ps, n, mt, heads);
   AGH_LAUNCH_CHECK();
   return AGH_OK;

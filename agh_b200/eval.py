@@ -34,9 +34,12 @@ def _eval_dataset(model, dataset, width, softmax_temp, opts, device):
     defer, model.defer_checks = model.defer_checks, True
     cost = []
     try:
+        done = 0
         for batch in iter_batches(dataset, opts.eval_batch_size, lo, hi, getattr(opts, 'no_progress_bar', True)):
             x = move_to(batch, device)
             B = x['loc'].size(0)
+            model.id_offset = lo + done          # Philox counters carry the global instance index (shard-independent)
+            done += B
             if opts.decode_strategy == 'greedy':
                 assert width == 0, 'Do not set width when using greedy'
                 assert opts.eval_batch_size <= opts.max_calc_batch_size, \
@@ -117,6 +120,8 @@ def get_parser():
 
 def main(argv=None):
     opts = get_parser().parse_args(argv)
+    if torch.cuda.is_available():          # the C ABI launches on the current device: one rank = one GPU
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
     if 'RANK' in os.environ and not torch.distributed.is_initialized():
         torch.distributed.init_process_group('nccl')
     random.seed(opts.seed)

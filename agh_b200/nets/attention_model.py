@@ -33,6 +33,20 @@ from .weights import pack_weights
 _TABLES = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'problems', 'agh', 'agh_tables.npz')
 
 
+def _on_model_device(fn):
+    """The C ABI launches on the CURRENT CUDA device: run the method with the model's device selected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kw):
+        dev = self._device()
+        if dev.type != 'cuda':
+            raise _lib.AghError('agh_b200 kernels need the model on a CUDA device (it is on %s); there is no CPU path' % dev)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kw)
+    return wrapper
+
+
 def set_decode_type(model, decode_type):
     if isinstance(model, (DataParallel, torch.nn.parallel.DistributedDataParallel)):
         model = model.module
@@ -91,7 +105,7 @@ class AttentionModel(nn.Module):
         self.check_tours = True          # run agh_get_costs' validity asserts like problem.get_costs does
         self.defer_checks = False        # collect the status words; raise_pending() syncs once
         self._pending_status = []
-        self.sampling_seed: Optional[int] = None   # fixed Philox seed (else drawn from torch's generator per call)
+        self._sampling_seed, self._seed_calls = None, 0   # fixed Philox seed (else drawn from torch's generator per call)
         self.id_offset = 0               # global id of instance 0 of the batch (sharding-independent sampling)
         self._blob = None
         self._blob_key = None
@@ -122,9 +136,22 @@ class AttentionModel(nn.Module):
             self._dist_dev = self.distance.to(dev).contiguous()
         return self._dist_dev
 
+    @property
+    def sampling_seed(self) -> Optional[int]:
+        return self._sampling_seed
+
+    @sampling_seed.setter
+    def sampling_seed(self, value: Optional[int]):
+        self._sampling_seed, self._seed_calls = value, 0
+
     def _seed(self) -> int:
-        if self.sampling_seed is not None:
-            return int(self.sampling_seed)
+        """Philox key of one sampling rollout.  A fixed sampling_seed is mixed with the number of rollouts drawn since
+        it was set (the 10 fleet forwards and the iter_rep iterations of sample_many must not reuse the same noise);
+        the first call returns the seed itself."""
+        if self._sampling_seed is not None:
+            s = (int(self._sampling_seed) + self._seed_calls * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+            self._seed_calls += 1
+            return s
         return int(torch.randint(0, 2 ** 62, (1,)).item())      # CPU generator: reproducible under torch.manual_seed
 
     def _mode(self) -> int:
@@ -143,6 +170,9 @@ class AttentionModel(nn.Module):
 
     def _raise_on_status(self, status: torch.Tensor):
         bad = int(status.max().item())
+        if bad & _lib.AGH_DECODE_STUCK:
+            raise AssertionError('decode did not terminate within 2N-1 steps: an instance has unvisited nodes that '
+                                 'are all infeasible (the reference loops forever on such an input)')
         if bad & _lib.AGH_TOUR_INVALID:
             raise AssertionError('Invalid tour')
         if bad & _lib.AGH_CAPACITY_EXCEEDED:
@@ -164,6 +194,7 @@ class AttentionModel(nn.Module):
         feat = torch.stack((task.demand, task.tw_left[:, 1:] / 1440, twr[:, 1:]), -1)
         return torch.cat((x[:, :1], x[:, 1:] + self.init_embed(feat)), 1)
 
+    @_on_model_device
     def embed(self, input) -> torch.Tensor:
         """a2+a3: node embeddings [B,n,128].  CUDA encoder in eval mode; torch graph in train mode."""
         task = self._as_task(input)
@@ -172,6 +203,7 @@ class AttentionModel(nn.Module):
         return ops.encode(self.weight_blob(), task)
 
     # ------------------------------------------------------------------ forward
+    @_on_model_device
     def forward(self, input, return_pi=False):
         """input: the reference's fleet-batch dict (or an ops.FleetTask).  Returns (cost, ll, serve_time[, pi])."""
         task = self._as_task(input)
@@ -191,14 +223,15 @@ class AttentionModel(nn.Module):
                              want_dumps=need_grad)
         self.last_steps = out['steps']
         cost, serve = out['cost'], out['serve']
+        status = out['status']           # AGH_DECODE_STUCK: the step budget ran out with unvisited nodes
         if self.check_tours:
             # problem.get_costs' asserts (attention_model.py:183) on the zero-padded int16 tours: no host sync
             # needed for the width; the status sync happens here, or once per batch when defer_checks is set
-            _, status = ops.get_costs(out['pi'], task, self.distance_table())
-            if self.defer_checks:
-                self._pending_status.append(status.max())
-            else:
-                self._raise_on_status(status)
+            status = status | ops.get_costs(out['pi'], task, self.distance_table())[1]
+        if self.defer_checks:
+            self._pending_status.append(status.max())
+        else:
+            self._raise_on_status(status)
         pi = None
         if return_pi or need_grad:
             T = int(out['steps'].max().item())
@@ -246,6 +279,7 @@ class AttentionModel(nn.Module):
         return (sel * valid).sum(1)
 
     # ------------------------------------------------------------------ reference-internal API kept for callers
+    @_on_model_device
     def _inner(self, input, embeddings):
         """(log_p [B,T,n], pi [B,T], serve_time) like attention_model.py:298-356 (materialises log_p: debugging only)."""
         task = self._as_task(input)
@@ -271,6 +305,7 @@ class AttentionModel(nn.Module):
         assert (log_p > -1000).data.all(), 'Logprobs should not be -inf, check sampling procedure!'
         return log_p.sum(1)
 
+    @_on_model_device
     def sample_many(self, input, batch_rep=1, iter_rep=1):
         """Best of batch_rep*iter_rep rollouts per instance (attention_model.py:358-370,
         utils/functions.py:182-223).  The encoder and the key projection run once per instance; the
@@ -281,12 +316,13 @@ class AttentionModel(nn.Module):
             blob = self.weight_blob()
             h = self.embed(task)
             keys, psc, qbase = ops.precompute(blob, h.contiguous(), task)
-            costs, pis, serves = [], [], []
+            costs, pis, serves, stuck = [], [], [], []
             for it in range(iter_rep):
                 out = ops.decode(blob, self.distance_table(), task, keys, psc, qbase, mode=self._mode(), temp=self.temp,
                                  seed=self._seed() if self.decode_type == 'sampling' else 0,
                                  id_offset=self.id_offset, reps=batch_rep)
                 costs.append(out['cost'].view(batch_rep, B)); pis.append(out['pi']); serves.append(out['serve'])
+                stuck.append(out['status'].max())
             R = batch_rep * iter_rep
             if R == 1:
                 mc, mp, ms = costs[0].view(B), pis[0], serves[0]
@@ -295,10 +331,11 @@ class AttentionModel(nn.Module):
                                             torch.cat(serves, 0).contiguous(), R, B)
             T = int((mp != 0).int().cumsum(1).argmax(1).max().item()) + 1 if mp.numel() else 0
             pi = mp[:, :max(T, 1)].long()
+            status = torch.stack(stuck).max()
             if self.check_tours:
-                _, status = ops.get_costs(mp, task, self.distance_table())
-                if self.defer_checks:
-                    self._pending_status.append(status.max())
-                else:
-                    self._raise_on_status(status)
+                status = torch.maximum(status, ops.get_costs(mp, task, self.distance_table())[1].max())
+            if self.defer_checks:
+                self._pending_status.append(status)
+            else:
+                self._raise_on_status(status)
         return pi, mc, ms

@@ -142,7 +142,8 @@ def precompute(wblob, h, task: FleetTask):
 
 def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.AGH_GREEDY, temp: float = 1.0,
            seed: int = 0, id_offset: int = 0, actions: Optional[torch.Tensor] = None, replay_steps: int = 0,
-           reps: int = 1, inject_logp: Optional[torch.Tensor] = None, want_logp_sel: bool = False,
+           reps: int = 1, inject_logp: Optional[torch.Tensor] = None, inject_z: Optional[torch.Tensor] = None,
+           want_logp_sel: bool = False,
            want_logp_full: bool = False, want_dumps: bool = False, t_stride: Optional[int] = None,
            smem_mats: int = 0):
     """a5-a12 + a14.  `reps` > 1 runs reps*B rollouts sharing the B key sets (sample_many)."""
@@ -150,10 +151,11 @@ def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.
     n = N + 1
     B = Bk * reps
     dev = keys.device
-    T = max(2 * N - 1, 1) if t_stride is None else t_stride
+    T = max(2 * N - 1, 2) if t_stride is None else t_stride      # N = 1: the node, then the depot
     out = {
         'pi': torch.empty(B, T, dtype=torch.int16, device=dev),
         'steps': torch.empty(B, dtype=torch.int32, device=dev),
+        'status': torch.empty(B, dtype=torch.int32, device=dev),
         'll': torch.empty(B, dtype=torch.float32, device=dev),
         'cost': torch.empty(B, dtype=torch.float32, device=dev),
         'serve': torch.empty(B, n, dtype=torch.float32, device=dev),
@@ -175,7 +177,8 @@ def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.
         duration=ptr(task.duration, torch.float64), distance=ptr(distance, torch.float32),
         wblob=ptr(wblob, torch.float32), key_mod=Bk if reps > 1 else 0, smem_mats=int(smem_mats), mode=mode, temp=float(temp),
         seed=int(seed) & (2 ** 64 - 1), id_offset=int(id_offset), actions=ptr(actions), replay_steps=int(replay_steps),
-        inject_logp=ptr(inject_logp), t_stride=T, pi=ptr(out['pi']), steps=ptr(out['steps']), ll=ptr(out['ll']),
+        inject_logp=ptr(inject_logp, torch.float32), inject_z=ptr(inject_z, torch.float32), t_stride=T, pi=ptr(out['pi']),
+        steps=ptr(out['steps']), status=ptr(out['status']), ll=ptr(out['ll']),
         cost=ptr(out['cost']), serve=ptr(out['serve']), logp_sel=ptr(out.get('logp_sel')),
         logp_full=ptr(out.get('logp_full')), mask_dump=ptr(out.get('mask_dump')), used_dump=ptr(out.get('used_dump')),
         cft_dump=ptr(out.get('cft_dump')), B=B, N=N)

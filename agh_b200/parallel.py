@@ -40,16 +40,23 @@ def all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat([bufs[r][:hi - lo] for r, (lo, hi) in enumerate(sizes)], 0)
 
 
-def allreduce_grads_(params) -> None:
-    """C1: average gradients across ranks through ONE flat f32 bucket (2.82 MB for this model)."""
+def allreduce_grads_(params, buffers=()) -> None:
+    """C1: average gradients across ranks through ONE flat f32 bucket (2.82 MB for this model).
+
+    `buffers`: floating-point module buffers (the BatchNorm running statistics) averaged in the same bucket, so that
+    every rank keeps identical weights AND identical eval-mode BatchNorm folds: train-mode BatchNorm uses per-rank batch
+    statistics (the reference's DataParallel semantics, graph_encoder.py:137-138), which would otherwise let the
+    running_mean / running_var of the ranks drift apart after the first step."""
     rank, ws = world()
     if ws == 1:
         return
-    grads = [p.grad for p in params if p.grad is not None]
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    tensors = [p.grad for p in params if p.grad is not None] + [b for b in buffers if b.is_floating_point()]
+    if not tensors:
+        return
+    flat = torch.cat([t.reshape(-1) for t in tensors])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat.div_(ws)
     off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()

@@ -85,6 +85,16 @@ class AGHDataset(Dataset):
             self.arrays = {k: v[offset:offset + num_samples] for k, v in arr.items()}
         self.size = self.arrays['loc'].size(0)
 
+    def __setstate__(self, state):
+        """Datasets pickled by the reference (inside a checkpoint's baseline, reinforce_baselines.py:228-233) hold a
+        list of per-instance dicts `data` (problem_agh.py:115): rebuild the per-field arrays from it."""
+        self.__dict__.update(state)
+        if 'arrays' not in state and 'data' in state:
+            data = state['data']
+            keys = ('loc', 'arrival', 'departure', 'type', 'demand')
+            self.arrays = {k: torch.stack([d[k] for d in data]) for k in keys} if len(data) else {}
+            self.size = len(data)
+
     def __len__(self):
         return self.size
 

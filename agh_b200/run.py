@@ -22,8 +22,8 @@ from .utils import load_problem, torch_load_cpu
 def run(opts):
     if not opts.use_cuda:
         raise RuntimeError('agh_b200 has no CPU path: a CUDA device is required')
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))      # the C ABI launches on the current device
     if 'RANK' in os.environ and not torch.distributed.is_initialized():
-        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
         torch.distributed.init_process_group('nccl')
     rank, _ = parallel.world()
     opts.device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))

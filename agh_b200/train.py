@@ -146,10 +146,13 @@ def train_epoch(model, optimizer, baseline, lr_scheduler, epoch, val_dataset, pr
     rank, ws = parallel.world()
     for batch_id, batch in enumerate(iter_batches(training_dataset, opts.batch_size,
                                                   no_progress_bar=opts.no_progress_bar)):
+        lo = 0
         if ws > 1:      # each rank trains on its slice of the global batch; gradients are averaged (C1)
             n_b = batch['baseline'].size(0)
             lo, hi = parallel.shard_bounds(n_b, rank, ws)
             batch = {'data': {k: v[lo:hi] for k, v in batch['data'].items()}, 'baseline': batch['baseline'][lo:hi]}
+        # Philox counters carry the GLOBAL instance index: ranks draw independent noise, results do not depend on G
+        get_inner_model(model).id_offset = batch_id * opts.batch_size + lo
         train_batch_agh(model, optimizer, baseline, epoch, batch_id, step, batch, tb_logger, opts)
         step += 1
 
@@ -184,7 +187,8 @@ def train_batch_agh(model, optimizer, baseline, epoch, batch_id, step, batch, tb
 
     optimizer.zero_grad()
     loss.backward()
-    parallel.allreduce_grads_([p for g in optimizer.param_groups for p in g['params']])
+    parallel.allreduce_grads_([p for g in optimizer.param_groups for p in g['params']],
+                              buffers=list(get_inner_model(model).buffers()))
     grad_norms = clip_grad_norms(optimizer.param_groups, opts.max_grad_norm)
     optimizer.step()
 

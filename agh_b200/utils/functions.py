@@ -17,7 +17,15 @@ def load_problem(name):
 
 
 def torch_load_cpu(load_path):
-    return torch.load(load_path, map_location='cpu', weights_only=False)
+    """torch.load on the CPU.  A checkpoint written by the reference pickles whole modules under the reference's
+    module paths (reinforce_baselines.py:228-233): when those do not resolve, the load is retried with the paths
+    aliased to this package's classes (utils/compat.py)."""
+    try:
+        return torch.load(load_path, map_location='cpu', weights_only=False)
+    except (ModuleNotFoundError, AttributeError):
+        from .compat import reference_module_aliases
+        with reference_module_aliases():
+            return torch.load(load_path, map_location='cpu', weights_only=False)
 
 
 def move_to(var, device):

@@ -99,22 +99,35 @@ def make_batch(B, N, seed):
 
 
 # ------------------------------------------------------------------------------------------------
+def cpu_reference(flights):
+    """The CPU implementation bench.py times beside the CUDA path: the UNMODIFIED reference (vendored under
+    baseline/_ref by oracle/vendor_reference.py) driven through its own train.rollout when present -- kind
+    "reference" -- else the oracle port, which reproduces it bit for bit (tests/test_oracle_golden.py) -- kind "port".
+    Returns (kind, fn(arrays) -> costs [B,10])."""
+    from oracle import reference_arm as RA
+    if RA.available() and os.environ.get('AGH_BENCH_PORT') != '1':
+        model = RA.make_model(1234)
+        return 'reference', lambda arrays: RA.rollout(model, arrays)
+    from oracle import agh_oracle as O
+    tb, W = O.Tables.load(), O.random_init_weights(1234)
+    return 'port', lambda arrays: O.rollout(W, tb, arrays)
+
+
 def run_reference(args):
-    """--impl reference: the reference algorithm on the host cores (oracle port; the Python reference
-    itself cannot travel to the GPU box).  Each step = one rollout of a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores (all threads).
+    Each step = one train.rollout of a bounded sample of the same workload."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    from oracle import agh_oracle as O
     # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to every rank)
     torch.set_num_threads(len(os.sched_getaffinity(0)))
-    tb, W = O.Tables.load(), O.random_init_weights(1234)
+    kind, ref_rollout = cpu_reference(args.flights)
     B = args.cpu_sample
     inst = make_batch(B, args.flights, 4321)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        costs = O.rollout(W, tb, inst)
+        costs = ref_rollout(inst)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
@@ -125,11 +138,37 @@ def run_reference(args):
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'AGH-%d greedy rollout, 10 fleets, random-init seed-1234 weights' % args.flights,
-                       'flights': args.flights, 'sample_batch': B},
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+                       'flights': args.flights, 'sample_batch': B,
+                       'implementation': 'unmodified reference train.rollout (baseline/_ref) on the CPU' if kind == 'reference'
+                       else 'oracle port of the reference (bit-equal results)'},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind, 'sample': sample},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'avg_cost': float(costs.sum(1).mean())}
     print(json.dumps(line))
+
+
+def exact_tour_match_rates(model, dev):
+    """Fraction of the seed-4321 validation instances whose 10 greedy fleet costs ALL equal the unmodified
+    reference's (golden fixtures in tests/golden, written by tests/golden/make_golden.py), and the mean-cost gap."""
+    import types as _t
+    from agh_b200 import AGHDataset
+    from agh_b200.train import rollout
+    out = {}
+    for N in (20, 50, 100):
+        path = os.path.join(ROOT, 'tests', 'golden', 'greedy_agh%d.npz' % N)
+        if not os.path.exists(path):
+            continue
+        g = np.load(path)
+        ds = AGHDataset.__new__(AGHDataset)
+        torch.utils.data.Dataset.__init__(ds)
+        ds.arrays, ds.size = make_batch(1000, N, 4321), 1000
+        opts = _t.SimpleNamespace(eval_batch_size=1000, device=dev, no_progress_bar=True, shard_across_ranks=False)
+        costs = rollout(model, ds, opts).numpy()
+        same = np.isclose(costs, g['costs'], rtol=1e-5, atol=0).all(1)
+        out['agh%d' % N] = {'exact_tour_match_rate': float(same.mean()), 'avg_cost': float(costs.sum(1).mean()),
+                            'reference_avg_cost': float(g['avg']),
+                            'rel_diff': float(abs(costs.sum(1).mean() - float(g['avg'])) / float(g['avg']))}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -282,20 +321,23 @@ def run_cuda(args):
             'decode_instance_steps_per_sec': total_inst_steps * ws / (ms_res * 1e-3),
             'avg_cost': float(host_costs.sum(1).mean()),
         }
+        line['exact_tour_match'] = exact_tour_match_rates(model, dev)
         if ws == 1 and not args.no_cpu_baseline:
-            from oracle import agh_oracle as O
-            tb, W = O.Tables.load(), O.random_init_weights(1234)
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+            kind, ref_rollout = cpu_reference(N)
             Bc = args.cpu_baseline_sample
             # the CPU path is fastest at a few hundred instances per call (68 inst/s at 256, 39 at 1024 on the 16-core
             # box: its per-step tensors fall out of cache), so the sample is rolled out in calls of 256
             chunks = [{k: v[s:s + 256].clone() for k, v in host.items()} for s in range(0, Bc, 256)]
             t0 = time.perf_counter()
-            ref = torch.cat([O.rollout(W, tb, c) for c in chunks], 0)
+            ref = torch.cat([ref_rollout(c) for c in chunks], 0)
             dt = time.perf_counter() - t0
-            line['cpu_baseline'] = {'value': Bc / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            mine = host_costs[:Bc]
+            same = torch.isclose(mine, ref, rtol=1e-5, atol=0).all(1).float().mean().item()
+            line['cpu_baseline'] = {'value': Bc / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind,
                                     'sample': 'first %d instances of the same batch in calls of 256, all 10 fleets, %.1f s' % (Bc, dt),
-                                    'avg_cost_same_instances': {'cpu': float(ref.sum(1).mean()),
-                                                                'gpu': float(host_costs[:Bc].sum(1).mean())}}
+                                    'avg_cost_same_instances': {'cpu': float(ref.sum(1).mean()), 'gpu': float(mine.sum(1).mean())},
+                                    'exact_tour_match_rate_same_instances': same}
         print(json.dumps(line))
     if ws > 1:
         dist.destroy_process_group()

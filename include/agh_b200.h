@@ -44,6 +44,9 @@ enum { AGH_GREEDY = 0, AGH_SAMPLING = 1, AGH_REPLAY = 2 };
 
 /* bits of the per-instance status word written by agh_get_costs (problem_agh.py:24-27,44,64) */
 enum { AGH_TOUR_INVALID = 1, AGH_CAPACITY_EXCEEDED = 2, AGH_TW_VIOLATED = 4 };
+/* bit of the per-instance status word written by agh_decode: the instance still had unvisited nodes when the step
+ * budget t_stride ran out (unvisited nodes that are all infeasible: the reference's Python loop would spin forever) */
+enum { AGH_DECODE_STUCK = 8 };
 
 const char* agh_last_error(void);
 int agh_version(void);
@@ -128,10 +131,13 @@ typedef struct {
   const int16_t* actions;  /* REPLAY: [B][t_stride] */
   int replay_steps;        /* REPLAY: steps to run for every instance */
   const float* inject_logp;/* optional [B][t_stride][n]: select from these log-probs instead */
-  int t_stride;            /* row stride (steps) of pi/actions/logp_sel/dumps; >= 2N-1 */
+  const float* inject_z;   /* optional [B][t_stride][n]: use these logits (after the tanh clipping, before the temperature
+                              and the mask) instead of the computed ones; everything downstream is the production path */
+  int t_stride;            /* row stride (steps) of pi/actions/logp_sel/dumps; >= max(2N-1, 2); also the step budget */
   /* outputs */
   int16_t* pi;             /* [B][t_stride], zero padded */
   int32_t* steps;          /* [B] steps until the instance finished */
+  int32_t* status;         /* optional [B]: 0, or AGH_DECODE_STUCK when the step budget ran out first */
   float* ll;               /* [B] sum of selected log-probs */
   float* cost;             /* [B] closed-tour length */
   float* serve;            /* [B][n] */

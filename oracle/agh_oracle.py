@@ -239,8 +239,13 @@ class Env:
 # --------------------------------------------------------------------------------------
 # a6-a11, a14: decode loop
 # --------------------------------------------------------------------------------------
-def step_log_p(W, h, fixed, env: Env, temp: float = 1.0):
-    """attention_model.py:429-451,510-522,550-584 for one step.  Returns (log_p [B,n], mask [B,n])."""
+def step_log_p(W, h, fixed, env: Env, temp: float = 1.0, inject_logits: Optional[torch.Tensor] = None,
+               logits_out: Optional[list] = None):
+    """attention_model.py:429-451,510-522,550-584 for one step.  Returns (log_p [B,n], mask [B,n]).
+
+    inject_logits [B,n]: replace the clipped logits (attention_model.py:580, before the mask and the
+    temperature) by these values -- the "given identical logits" experiments; logits_out collects the
+    clipped logits of the step."""
     fixed_ctx, fleet_emb, gK, gV, LK = fixed
     B, n, D = h.shape
     ctx = torch.cat((h.gather(1, env.prev[:, :, None].expand(B, 1, D)),
@@ -254,16 +259,23 @@ def step_log_p(W, h, fixed, env: Env, temp: float = 1.0):
     glimpse = F.linear(heads.permute(1, 2, 3, 0, 4).contiguous().view(-1, 1, 1, D), W['project_out.weight'])
     logits = torch.matmul(glimpse, LK.transpose(-2, -1)).squeeze(-2) / math.sqrt(D)
     logits = torch.tanh(logits) * 10.0
+    if logits_out is not None:
+        logits_out.append(logits[:, 0, :].detach().clone())
+    if inject_logits is not None:
+        logits = inject_logits[:, None, :].clone()
     logits[mask[:, None, :]] = -math.inf
     return torch.log_softmax(logits / temp, dim=-1)[:, 0, :], mask
 
 
 def decode(W, task, h, mode: str = 'greedy', actions: Optional[torch.Tensor] = None, temp: float = 1.0,
-           record: Optional[dict] = None, inject_log_p: Optional[torch.Tensor] = None):
+           record: Optional[dict] = None, inject_log_p: Optional[torch.Tensor] = None,
+           inject_logits: Optional[torch.Tensor] = None):
     """attention_model.py:298-356.  mode: 'greedy' | 'sampling' | 'replay' (follow `actions` [B,T]).
 
     inject_log_p [B,T,n]: use these log-probs for SELECTION instead of the computed ones
-    ("identical logits" experiments).  Returns dict(pi, ll, serve, lengths, logp_sel [B,T]).
+    ("identical logits" experiments); inject_logits [B,T,n]: replace the clipped logits of step t, the
+    log-softmax / exp / argmax that follow are the reference's.  record['logits'] collects the clipped logits.
+    Returns dict(pi, ll, serve, lengths, logp_sel [B,T]).
     """
     env = Env(task)
     fixed = precompute(W, h, task['fleet'])
@@ -275,7 +287,9 @@ def decode(W, task, h, mode: str = 'greedy', actions: Optional[torch.Tensor] = N
                 break
         elif env.all_finished():
             break
-        log_p, mask = step_log_p(W, h, fixed, env, temp)
+        log_p, mask = step_log_p(W, h, fixed, env, temp,
+                                 inject_logits=None if inject_logits is None else inject_logits[:, t],
+                                 logits_out=None if record is None else record.setdefault('logits', []))
         if record is not None:
             record.setdefault('log_p', []).append(log_p.detach())
             record.setdefault('mask', []).append(mask)

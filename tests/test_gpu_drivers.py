@@ -216,3 +216,30 @@ def test_edge_cases_empty_single_and_oversized(cuda_model):
         task = ops.fleet_task(big['loc'], big['type'], big['departure'], big['demand'], lv, 0, 1, info['duration'][1],
                               info['next_duration'][0], nd_is_f32=False)
         ops.encode(cuda_model.weight_blob(), task)
+
+
+def test_resume_from_reference_checkpoint(tmp_path, weights):
+    """f4: an epoch-*.pt as the UNMODIFIED reference writes it (pickled-module baseline + pickled AGHDataset,
+    reinforce_baselines.py:228-233; fixture from tests/golden/make_ref_checkpoint.py) resumes: load_model reads the
+    directory, RolloutBaseline.load_state_dict restores the baseline model and its dataset, and a rollout runs."""
+    import shutil
+    from agh_b200 import AGH
+    from agh_b200.reinforce_baselines import RolloutBaseline
+    from agh_b200.utils import load_model, torch_load_cpu
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_checkpoint_epoch-3.pt')
+    shutil.copy(src, tmp_path / 'epoch-3.pt')
+    json.dump(ARGS_JSON, open(tmp_path / 'args.json', 'w'))
+    model, _ = load_model(str(tmp_path))
+    model = model.cuda()
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), weights[k]), k
+    ck = torch_load_cpu(str(tmp_path / 'epoch-3.pt'))
+    opts = _train_opts(tmp_path, val_size=4)
+    baseline = RolloutBaseline(model, AGH, opts)
+    baseline.load_state_dict(ck['baseline'])
+    assert baseline.epoch == 3 and len(baseline.dataset) == 4 and baseline.bl_vals.shape == (4,)
+    for k, v in baseline.model.state_dict().items():
+        assert torch.equal(v.cpu(), weights[k]), k
+    optimizer = torch.optim.Adam([{'params': model.parameters(), 'lr': 1e-4}])
+    optimizer.load_state_dict(ck['optimizer'])
+    torch.set_rng_state(ck['rng_state'])

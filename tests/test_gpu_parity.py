@@ -131,6 +131,124 @@ def test_greedy_bit_exact_given_identical_logits(cuda_model, tables, n):
         assert np.array_equal(out['serve'].cpu().numpy(), g['serve'][:S, k])
 
 
+def oracle_fleet_records(tables, weights, inst, fleets=None):
+    """Greedy oracle rollout of `inst` (all 10 fleets, the oracle's own serve-time chain) with per-step dumps.
+    Yields (k, task_cpu, out, rec) for the fleets in `fleets` (positions in tables.order; default all)."""
+    lv = O.new_tw_left_levels(inst)
+    with torch.no_grad():
+        for k, f in enumerate(tables.order):
+            task = O.fleet_task(tables, inst, f, lv)
+            rec = {}
+            out = O.forward(weights, task, record=rec)
+            if fleets is None or k in fleets:
+                yield k, task, out, rec
+            O.chain_tw_left(tables, lv, f, out['serve'])
+
+
+@pytest.mark.parametrize('n,B', [(100, 256), (200, 64), (300, 64)])
+def test_replay_oracle_actions_wide(cuda_model, tables, weights, n, B):
+    """Bit-exact environment at the headline size and beyond: hundreds of instances x all 10 fleets.  The pinned
+    oracle (bit-equal to the reference, tests/test_oracle_golden.py) produces the per-step dumps at test time; the
+    kernel replays its tours: masks, used capacity, cur_free_time and serve_time must be identical in every bit,
+    log-probs within 1e-4, costs within 1e-5."""
+    from agh_b200 import _lib
+    inst = {k: v[:B] for k, v in make_instances(n).items()}
+    Tmax = 2 * n - 1
+    checked = 0
+    for k, task_cpu, out, rec in oracle_fleet_records(tables, weights, inst):
+        T = out['pi'].size(1)
+        acts = torch.zeros(B, Tmax, dtype=torch.int16)
+        acts[:, :T] = out['pi'].to(torch.int16)
+        mine = cuda_forward(cuda_model, to_task(task_cpu), mode=_lib.AGH_REPLAY, actions=acts.cuda(), replay_steps=T,
+                            want_logp_full=True, want_dumps=True)
+        mask = unpack_mask(mine['mask_dump'][:, :T], n + 1).cpu()
+        assert torch.equal(mask, torch.stack(rec['mask'], 1)), 'feasibility mask differs (N=%d fleet idx %d)' % (n, k)
+        assert torch.equal(mine['used_dump'][:, :T].cpu(), torch.stack(rec['used'], 1))
+        assert torch.equal(mine['cft_dump'][:, :T].cpu(), torch.stack(rec['cft'], 1).double())
+        assert torch.equal(mine['serve'].cpu(), out['serve']), 'serve_time differs'
+        assert_logp_close(mine['logp_full'][:, :T].cpu().numpy(), torch.stack(rec['log_p'], 1).numpy(),
+                          'N=%d fleet idx %d' % (n, k))
+        assert np.allclose(mine['ll'].cpu().numpy(), out['ll'].numpy(), rtol=LOGP_RTOL, atol=1e-4)
+        assert np.allclose(mine['cost'].cpu().numpy(), out['cost'].numpy(), rtol=COST_RTOL, atol=0)
+        checked += mask.numel()
+    print('N=%d: %d mask bits, %d instance-fleets bit-exact' % (n, checked, 10 * B))
+
+
+@pytest.mark.parametrize('n,B', [(20, 128), (50, 64), (100, 32)])
+def test_greedy_production_branch_given_identical_logits(cuda_model, tables, weights, n, B):
+    """north_star: "greedy tours bit-exact given identical logits".  The reference's clipped logits (from the pinned
+    oracle) are injected into the kernel's PRODUCTION greedy branch (inject_z: same sum-exp, same selection code as a
+    normal rollout, including the near-tie re-decision): tours and serve times must equal the reference's exactly."""
+    from agh_b200 import _lib
+    inst = {k: v[:B] for k, v in make_instances(n).items()}
+    Tmax = 2 * n - 1
+    for k, task_cpu, out, rec in oracle_fleet_records(tables, weights, inst, fleets=(0, 3, 9)):
+        T = out['pi'].size(1)
+        z = torch.zeros(B, Tmax, n + 1)
+        z[:, :T] = torch.stack(rec['logits'], 1)
+        mine = cuda_forward(cuda_model, to_task(task_cpu), mode=_lib.AGH_GREEDY, inject_z=z.cuda())
+        assert torch.equal(mine['pi'][:, :T].cpu().long(), out['pi']), 'tour differs (N=%d fleet idx %d)' % (n, k)
+        assert torch.equal(mine['serve'].cpu(), out['serve'])
+        assert int(mine['status'].max()) == 0
+
+
+@pytest.mark.parametrize('temp', [1.0, 2.0])
+def test_greedy_near_ties_and_duplicates(cuda_model, tables, weights, temp):
+    """Constructed logits: at every step the feasible nodes carry values that are equal (duplicate flights), 1-3 ulp
+    apart at |z| < 1/32 (far below the rounding grid of log_p, so the reference's exp(log_p) collapses them into a tie
+    and takes the FIRST index -- selecting on z itself would take the largest), or well separated.  The production
+    branch must follow the reference's argmax(exp(log_softmax(z)))."""
+    from agh_b200 import _lib
+    n, B = 20, 256
+    inst = {k: v[:B] for k, v in make_instances(n).items()}
+    task_cpu = O.fleet_task(tables, inst, 2, O.new_tw_left_levels(inst))
+    Tmax = 2 * n - 1
+    rng = np.random.RandomState(11)
+    base = rng.uniform(2.0 ** -6, 2.0 ** -5 * 0.99, size=(B, Tmax, 1)).astype(np.float32)
+    ulps = rng.randint(0, 4, size=(B, Tmax, n + 1))
+    kind = rng.randint(0, 3, size=(B, Tmax, 1))
+    near = (base.view(np.int32) + ulps.astype(np.int32)).view(np.float32)                         # 0..3 ulp above base
+    far = (base + rng.uniform(-5, 5, size=(B, Tmax, n + 1))).astype(np.float32)  # decisive gaps
+    top = rng.rand(B, Tmax, n + 1) < 0.3                                         # a near-tied cluster on top of a far field
+    mixed = np.where(top, near + np.float32(6.0), far)
+    z = torch.from_numpy(np.where(kind == 0, near, np.where(kind == 1, far, mixed)).astype(np.float32)) * temp
+    with torch.no_grad():
+        h = O.encoder(weights, O.init_embed(weights, task_cpu))
+        ref = O.decode(weights, task_cpu, h, mode='greedy', temp=temp, inject_logits=z, record=(rec := {}))
+    T = ref['pi'].size(1)
+    mine = cuda_forward(cuda_model, to_task(task_cpu), mode=_lib.AGH_GREEDY, inject_z=z.cuda(), temp=temp)
+    assert torch.equal(mine['pi'][:, :T].cpu().long(), ref['pi'])
+    assert torch.equal(mine['serve'].cpu(), ref['serve'])
+    # the test has teeth: in many steps the reference's choice is NOT the largest logit (it is the first index of a
+    # collapsed tie), so a kernel selecting on z itself would produce different tours
+    zt = z[:, :T].masked_fill(torch.stack(rec['mask'], 1), -np.inf)
+    not_largest = (zt.gather(2, ref['pi'][:, :, None]).squeeze(-1) < zt.max(2)[0]).sum().item()
+    assert not_largest > 100, not_largest
+
+
+def test_decode_step_budget_and_status(cuda_model, tables):
+    """An instance whose unvisited nodes are all infeasible (here: demand above the capacity) cannot finish: the
+    reference would loop forever, the kernel stops at the step budget and flags AGH_DECODE_STUCK; N = 1 takes two
+    steps (the node, then the depot) and writes inside its own pi row."""
+    from agh_b200 import _lib, ops
+    inst = {k: v[:4].clone() for k, v in make_instances(20).items()}
+    inst['demand'][1, :, 5] = 1.5
+    task_cpu = O.fleet_task(tables, inst, 1, O.new_tw_left_levels(inst))
+    out = cuda_forward(cuda_model, to_task(task_cpu), mode=_lib.AGH_GREEDY)
+    st = out['status'].cpu().tolist()
+    assert st == [0, _lib.AGH_DECODE_STUCK, 0, 0]
+    assert int(out['steps'][1]) == 39
+    cuda_model.set_decode_type('greedy')
+    with pytest.raises(AssertionError, match='did not terminate'):
+        cuda_model(to_task(task_cpu))
+    # N = 1
+    one = {k: (v[:5, :, :1] if k == 'demand' else v[:5, :1]).contiguous() for k, v in make_instances(20).items()}
+    t1 = O.fleet_task(tables, one, 1, O.new_tw_left_levels(one))
+    o1 = cuda_forward(cuda_model, to_task(t1), mode=_lib.AGH_GREEDY)
+    assert o1['pi'].shape == (5, 2) and o1['pi'].cpu().tolist() == [[1, 0]] * 5
+    assert o1['steps'].cpu().tolist() == [2] * 5 and int(o1['status'].max()) == 0
+
+
 def _rollout(model, arrays, bs=1000):
     from agh_b200.train import rollout
     from agh_b200 import AGHDataset
@@ -141,64 +259,79 @@ def _rollout(model, arrays, bs=1000):
     return rollout(model, ds, opts)
 
 
-def test_greedy_end_to_end_agh20(cuda_model, tables, weights):
-    """Config C1 (AGH-20, batch 1000).  Greedy tours are chaotic in the logits, so:
-    (i) most instances reproduce all 10 reference costs, (ii) the mean cost agrees, (iii) every first
-    divergence happens at a step whose top-2 probability gap is below the fp32 noise floor."""
-    g = load_golden('greedy_agh20.npz')
-    inst = make_instances(20)
-    costs = _rollout(cuda_model, inst).numpy()
-    same = np.isclose(costs, g['costs'], rtol=COST_RTOL, atol=0).all(1)
-    print('AGH-20: instances with all fleet costs equal: %.4f; mean %.3f vs %.3f' % (same.mean(), costs.sum(1).mean(), g['avg']))
-    assert same.mean() > 0.90
-    assert abs(costs.sum(1).mean() - float(g['avg'])) / float(g['avg']) < 2e-3
-    # (iii) trace mismatches: replay with the oracle and look at the gap at the first differing step
-    bad = np.nonzero(~same)[0][:24]
-    if len(bad):
-        from agh_b200.train import fleet_rollout
-        sub = {k: v[bad] for k, v in inst.items()}
-        pis = []
-        cuda_model.set_decode_type('greedy')
-        orig = cuda_model.forward
-        def fwd(task, return_pi=False):
-            c, l, s, p = orig(task, return_pi=True)
-            pis.append(p.cpu())
-            return c, l, s
-        cuda_model.forward = fwd
-        try:
-            with torch.no_grad():
-                fleet_rollout(cuda_model, sub, torch.device('cuda'))
-        finally:
-            del cuda_model.forward
-        lv = O.new_tw_left_levels(sub)
-        alive = np.ones(len(bad), bool)
+# Every greedy divergence from the reference must happen at a step whose top-2 probability gap (in the reference's
+# own log-probs) is below this bound.  The kernel's log-prob error is ~1e-6, so a decision
+# whose gap exceeds 1e-5 cannot flip.
+GAP_TOL = 1e-5
+# floors for the fraction of instances whose 10 fleet costs ALL equal the reference's, and the measured rates
+# (B200, seed-4321 validation sets, random-init seed-1234 weights) are recorded in DESIGN.md section 5
+MATCH_FLOOR = {20: 0.97, 50: 0.93, 100: 0.88}
+MEAN_RTOL = 2e-5
+
+
+def trace_divergences(model, tables, weights, sub):
+    """Roll `sub` out on the GPU and through the oracle fleet by fleet; for every instance return the top-2 gap
+    (reference probabilities) at the first step where the tours differ, or None when all 10 tours are equal."""
+    from agh_b200.train import fleet_rollout
+    pis = []
+    model.set_decode_type('greedy')
+    orig = model.forward
+
+    def fwd(task, return_pi=False):
+        c, l, s, p = orig(task, return_pi=True)
+        pis.append(p.cpu())
+        return c, l, s
+    model.forward = fwd
+    try:
         with torch.no_grad():
-            for k, f in enumerate(tables.order):
-                task = O.fleet_task(tables, sub, f, lv)
-                rec = {}
-                out = O.forward(weights, task, record=rec)
-                mine, ref = pis[k].numpy(), out['pi'].numpy()
-                T = min(mine.shape[1], ref.shape[1])
-                for r in np.nonzero(alive)[0]:
-                    d = np.nonzero(mine[r, :T] != ref[r, :T])[0]
-                    if len(d):
-                        p = rec['log_p'][d[0]][r].exp()
-                        gap = (p[ref[r, d[0]]] - p[mine[r, d[0]]]).item()
-                        assert 0 <= gap < 1e-4, 'instance %d diverged at a decisive step (gap %.3e)' % (bad[r], gap)
-                        alive[r] = False
-                O.chain_tw_left(tables, lv, f, out['serve'])
-        assert not alive.any() or True
+            fleet_rollout(model, sub, torch.device('cuda'), level_batch=False)
+    finally:
+        del model.forward
+    B = sub['loc'].size(0)
+    lv = O.new_tw_left_levels(sub)
+    gaps = [None] * B
+    alive = np.ones(B, bool)
+    with torch.no_grad():
+        for k, f in enumerate(tables.order):
+            task = O.fleet_task(tables, sub, f, lv)
+            rec = {}
+            out = O.forward(weights, task, record=rec)
+            mine, ref = pis[k].numpy(), out['pi'].numpy()
+            T = max(mine.shape[1], ref.shape[1])
+            mine = np.pad(mine, ((0, 0), (0, T - mine.shape[1])))
+            ref = np.pad(ref, ((0, 0), (0, T - ref.shape[1])))
+            for r in np.nonzero(alive)[0]:
+                d = np.nonzero(mine[r] != ref[r])[0]
+                if len(d):
+                    p = rec['log_p'][d[0]][r].exp()
+                    gaps[r] = (p[ref[r, d[0]]] - p[mine[r, d[0]]]).item()
+                    alive[r] = False           # later fleets of this instance see different time windows
+            O.chain_tw_left(tables, lv, f, out['serve'])
+    return gaps
 
 
-@pytest.mark.parametrize('n', [50, 100])
-def test_greedy_end_to_end_larger(cuda_model, n):
+@pytest.mark.parametrize('n', [20, 50, 100])
+def test_greedy_end_to_end(cuda_model, tables, weights, n):
+    """Configs C1 (AGH-20, batch 1000), C2 and C3 instances against the reference's golden costs.  Greedy tours are
+    chaotic in the logits, so: (i) the fraction of instances that reproduce ALL 10 reference fleet
+    costs is above a floor, (ii) the mean cost agrees to 2e-5, (iii) every divergence is traced to its first differing
+    step, and the reference's top-2 probability gap there is below the fp32 noise bound GAP_TOL."""
     g = load_golden('greedy_agh%d.npz' % n)
     inst = make_instances(n)
     costs = _rollout(cuda_model, inst).numpy()
     same = np.isclose(costs, g['costs'], rtol=COST_RTOL, atol=0).all(1)
-    print('AGH-%d: instances with all fleet costs equal: %.4f; mean %.3f vs %.3f' % (n, same.mean(), costs.sum(1).mean(), g['avg']))
-    assert np.isclose(costs[:, 0], g['costs'][:, 0], rtol=COST_RTOL, atol=0).mean() > 0.9
-    assert abs(costs.sum(1).mean() - float(g['avg'])) / float(g['avg']) < 5e-3
+    mean, ref_mean = costs.sum(1).mean(), float(g['avg'])
+    print('AGH-%d: exact_tour_match_rate (all 10 fleet costs equal) %.4f; mean %.3f vs %.3f (rel %.2e)'
+          % (n, same.mean(), mean, ref_mean, abs(mean - ref_mean) / ref_mean))
+    assert same.mean() >= MATCH_FLOOR[n]
+    assert abs(mean - ref_mean) / ref_mean < MEAN_RTOL
+    bad = np.nonzero(~same)[0][:32 if n <= 50 else 12]
+    if len(bad):
+        gaps = trace_divergences(cuda_model, tables, weights, {k: v[bad] for k, v in inst.items()})
+        print('AGH-%d: top-2 gaps at the first divergence: %s' % (n, ' '.join('%.1e' % x for x in gaps if x is not None)))
+        for r, gap in zip(bad, gaps):
+            assert gap is not None, 'instance %d: costs differ but all tours are equal' % r
+            assert 0 <= gap < GAP_TOL, 'instance %d diverged at a decisive step (gap %.3e)' % (r, gap)
 
 
 def test_shard_invariance(cuda_model):
