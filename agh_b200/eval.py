@@ -32,6 +32,7 @@ def _eval_dataset(model, dataset, width, softmax_temp, opts, device):
     rank, ws = parallel.world()
     lo, hi = parallel.shard_bounds(len(dataset), rank, ws)
     defer, model.defer_checks = model.defer_checks, True
+    id_offset0 = model.id_offset
     cost = []
     try:
         done = 0
@@ -72,7 +73,7 @@ def _eval_dataset(model, dataset, width, softmax_temp, opts, device):
             model.raise_pending()
             cost.append(torch.cat(batch_cost, 1))
     finally:
-        model.defer_checks = defer
+        model.defer_checks, model.id_offset = defer, id_offset0
     local = torch.cat(cost, 0) if cost else torch.zeros(0, 10, device=device)
     if ws > 1:
         local = parallel.all_gather_rows(local, len(dataset))

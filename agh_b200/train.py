@@ -144,6 +144,7 @@ def train_epoch(model, optimizer, baseline, lr_scheduler, epoch, val_dataset, pr
     model.train()
     set_decode_type(model, 'sampling')
     rank, ws = parallel.world()
+    id_offset0 = get_inner_model(model).id_offset
     for batch_id, batch in enumerate(iter_batches(training_dataset, opts.batch_size,
                                                   no_progress_bar=opts.no_progress_bar)):
         lo = 0
@@ -155,6 +156,7 @@ def train_epoch(model, optimizer, baseline, lr_scheduler, epoch, val_dataset, pr
         get_inner_model(model).id_offset = batch_id * opts.batch_size + lo
         train_batch_agh(model, optimizer, baseline, epoch, batch_id, step, batch, tb_logger, opts)
         step += 1
+    get_inner_model(model).id_offset = id_offset0
 
     epoch_duration = time.time() - start_time
     print('Finished epoch {}, took {} s'.format(epoch, time.strftime('%H:%M:%S', time.gmtime(epoch_duration))))

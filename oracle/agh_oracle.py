@@ -249,7 +249,7 @@ def step_log_p(W, h, fixed, env: Env, temp: float = 1.0, inject_logits: Optional
     fixed_ctx, fleet_emb, gK, gV, LK = fixed
     B, n, D = h.shape
     ctx = torch.cat((h.gather(1, env.prev[:, :, None].expand(B, 1, D)),
-                     CAPACITY - env.used[:, :, None], env.cft[:, :, None] / 1440), -1).float()
+                     CAPACITY - env.used[:, :, None], env.cft[:, :, None] / 1440), -1).float().to(h.dtype)
     query = fixed_ctx + F.linear(ctx, W['project_step_context.weight']) + fleet_emb
     mask = env.mask()
     gQ = query.view(B, 1, N_HEADS, 1, D // N_HEADS).permute(2, 0, 1, 3, 4)
