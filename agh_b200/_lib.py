@@ -65,7 +65,7 @@ class DecodeArgs(C.Structure):
     _fields_ = [
         ('keys', C.c_void_p), ('psc', C.c_void_p), ('qbase', C.c_void_p), ('coord', C.c_void_p),
         ('demand', C.c_void_p), ('tw_left', C.c_void_p), ('tw_right', C.c_void_p), ('duration', C.c_void_p),
-        ('distance', C.c_void_p), ('wblob', C.c_void_p),
+        ('distance', C.c_void_p), ('travel', C.c_void_p), ('wblob', C.c_void_p),
         ('key_mod', C.c_int), ('smem_mats', C.c_int), ('mode', C.c_int), ('temp', C.c_float), ('seed', C.c_uint64), ('id_offset', C.c_int64),
         ('actions', C.c_void_p), ('replay_steps', C.c_int), ('inject_logp', C.c_void_p), ('inject_z', C.c_void_p),
         ('t_stride', C.c_int),

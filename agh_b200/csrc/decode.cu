@@ -78,6 +78,28 @@ __device__ __forceinline__ float gumbel(uint64_t seed, uint64_t id, uint32_t ste
   return -logf(-logf(fminf(u, 0.99999994f)));
 }
 
+// Packed FP32 pairs (sm_100a fma.rn.f32x2 -> SASS FFMA2): two IEEE FMAs per issued instruction.  Measured on B200
+// (tools/micro/ffma2.cu) the FP32 FLOP rate is the same as FFMA's, so the gain is issue slots and chain length: the
+// 16-term dot products below are 8 dependent FFMA2 instead of 16 dependent FFMA.
+__device__ __forceinline__ uint64_t pack2(float x, float y) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ float sum2(uint64_t v) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+  return x + y;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
   return acc;
@@ -112,72 +134,100 @@ constexpr float NEAR_TIE = 2e-6f;
 enum { RES_V = 1, RES_L = 2, RES_P = 4 };
 
 struct DecodeSmem {
-  // byte offsets into dynamic shared memory
-  size_t V, L, P, twr, dur, twl, dem, crd, dcur, z, serve, o, qb, wc, wt, red, mw, idx, fin, bar, total;
+  // byte offsets into dynamic shared memory.  The small per-step arrays come FIRST, at offsets that depend on the
+  // template parameter NPL only (compile-time immediates in the step loop); the key matrices follow.
+  size_t twr, dur, twl, dem, crd, dcur, z, serve, o, qb, red, mw, idx, fin, bar, V, L, P, total;
 };
 
+__host__ __device__ constexpr size_t al16(size_t b) { return (b + 15) & ~(size_t)15; }
+
 __host__ __device__ inline DecodeSmem decode_smem_layout(int n, int npl, int res) {
-  DecodeSmem s;
+  DecodeSmem s{};
   const size_t npad = (size_t)npl * 32;
   size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  auto take = [&](size_t bytes) { size_t o = off; off += al16(bytes); return o; };
+  s.o = take(D * 4); s.qb = take(D * 4);          // qb slot holds the step's query vector
+  s.red = take(8 * 4 * 4);
+  s.mw = take(16 * 4);
+  s.bar = take(16);
+  s.z = take(npad * 4); s.dcur = take(2 * npad * 4);
+  s.fin = take(2 * npad * 8);                     // finish time of every node if it were served next (f64), double-buffered
+  s.dem = take(npad * 4); s.crd = take(npad * 4); s.serve = take(npad * 4);
+  s.idx = take(npad * 2);                         // compact list of the step's feasible nodes (u16)
+  s.twr = take(npad * 8); s.dur = take(npad * 8); s.twl = take(npad * 4);
+  off = (off + 127) & ~(size_t)127;
   s.V = take((res & RES_V) ? (size_t)n * KS * 4 : 0);
   s.L = take((res & RES_L) ? (size_t)n * KS * 4 : 0);
   s.P = take((res & RES_P) ? (size_t)n * D * 4 : 0);
-  s.twr = take(npad * 8); s.dur = take(npad * 8);
-  s.twl = take(npad * 4); s.dem = take(npad * 4); s.crd = take(npad * 4);
-  s.dcur = take(2 * npad * 4); s.z = take(npad * 4); s.serve = take(npad * 4);
-  s.o = take(D * 4); s.qb = take(D * 4); s.wc = 0; s.wt = 0;       // qb slot holds the step's query vector
-  s.red = take(8 * 4 * 4);
-  s.mw = take(16 * 4);
-  s.idx = take(npad * 2);                       // compact list of the step's feasible nodes (u16)
-  s.fin = take(2 * npad * 8);                   // finish time of every node if it were served next (f64), double-buffered
-  s.bar = take(16);
   s.total = off;
   return s;
 }
 
-// Key rows are held in shared memory unpadded ([n][128] f32) with the 16-byte chunks of every aligned 8-chunk group
-// XOR-swizzled by (node & 7): lanes that read the same logical chunk of 8 consecutive nodes hit 8
-// different bank groups, so every LDS.128 below is conflict-free without padding bytes.
-__device__ __forceinline__ int swz(int chunk, int node) { return (chunk & ~7) | ((chunk ^ node) & 7); }
+// compile-time offsets of the small arrays (must mirror decode_smem_layout)
+template <int NPL>
+struct SmallOff {
+  static constexpr size_t npad = (size_t)NPL * 32;
+  static constexpr size_t o = 0;
+  static constexpr size_t qb = o + al16(D * 4);
+  static constexpr size_t red = qb + al16(D * 4);
+  static constexpr size_t mw = red + al16(8 * 4 * 4);
+  static constexpr size_t bar = mw + al16(16 * 4);
+  static constexpr size_t z = bar + al16(16);
+  static constexpr size_t dcur = z + al16(npad * 4);
+  static constexpr size_t fin = dcur + al16(2 * npad * 4);
+  static constexpr size_t dem = fin + al16(2 * npad * 8);
+  static constexpr size_t crd = dem + al16(npad * 4);
+  static constexpr size_t serve = crd + al16(npad * 4);
+  static constexpr size_t idx = serve + al16(npad * 4);
+  static constexpr size_t twr = idx + al16(npad * 2);
+  static constexpr size_t dur = twr + al16(npad * 8);
+  static constexpr size_t twl = dur + al16(npad * 8);
+  static constexpr size_t mats = (twl + al16(npad * 4) + 127) & ~(size_t)127;
+};
+
+// V rows (and, on the compact path, LK' rows) are held in shared memory unpadded ([n][128] f32) with the 16-byte chunks
+// of every aligned 8-chunk group XOR-swizzled by (node & 7): lanes that read the same logical chunk of 8 consecutive
+// nodes hit 8 different bank groups, so every LDS.128 is conflict-free without padding bytes.
+__device__ __forceinline__ int swz(int chunk, int node) { return chunk ^ (node & 7); }
 
 // resident CTAs per SM the register budget is compiled for (65536 / (256 * regs))
 constexpr int decode_min_blocks(int npl) { return npl == 1 ? 3 : (npl <= 4 ? 2 : 1); }
 
-// NPL: nodes per lane in the glimpse (ceil(n/32)); RES: which of {V, LK', P_sc} live in smem.
-template <int NPL, int RES>
+// NPL: nodes per lane in the glimpse (ceil(n/32)); RES: which of {V, LK', P_sc} live in smem; DBG: the variant that
+// carries the optional paths (replay, logit / log-prob injection, per-step dumps, full log-prob output) -- the
+// production greedy / sampling rollout is compiled without them.
+template <int NPL, int RES, bool DBG>
 __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(const agh_decode_args a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int n = a.N + 1;
   const int b = blockIdx.x;
   const int kb = a.key_mod > 0 ? b % a.key_mod : b;      // source of keys / node vectors
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const DecodeSmem L = decode_smem_layout(n, NPL, RES);
+  using SO = SmallOff<NPL>;
   constexpr int NPAD = NPL * 32;
   constexpr int MPT = (NPAD + 255) / 256;                 // mask nodes per thread (node = tid + 256 k)
   // large graphs walk a compact list of the feasible nodes in the value / logit phases (measured: N = 300 +41 %,
   // N = 200 +3 %, N <= 100 -4 %: there the fully unrolled fixed mapping wins)
   constexpr bool COMPACT = NPL > 4;
 
-  float* sV = reinterpret_cast<float*>(smem + L.V);
-  float* sL = reinterpret_cast<float*>(smem + L.L);
-  float* sP = reinterpret_cast<float*>(smem + L.P);
-  double* s_twr = reinterpret_cast<double*>(smem + L.twr);
-  double* s_dur = reinterpret_cast<double*>(smem + L.dur);
-  float* s_twl = reinterpret_cast<float*>(smem + L.twl);
-  float* s_dem = reinterpret_cast<float*>(smem + L.dem);
-  int* s_crd = reinterpret_cast<int*>(smem + L.crd);
-  float* s_dcur = reinterpret_cast<float*>(smem + L.dcur);
-  float* s_z = reinterpret_cast<float*>(smem + L.z);
-  float* s_serve = reinterpret_cast<float*>(smem + L.serve);
-  float* s_o = reinterpret_cast<float*>(smem + L.o);
-  float* s_q = reinterpret_cast<float*>(smem + L.qb);        // query of the current step, written by threads 128..255
-  float* s_red = reinterpret_cast<float*>(smem + L.red);
-  uint32_t* s_mw = reinterpret_cast<uint32_t*>(smem + L.mw);
-  uint16_t* s_idx = reinterpret_cast<uint16_t*>(smem + L.idx);
-  double* s_fin = reinterpret_cast<double*>(smem + L.fin);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+  float* sV = reinterpret_cast<float*>(smem + SO::mats);
+  float* sL = sV + ((RES & RES_V) ? (size_t)n * KS : 0);
+  float* sP = sL + ((RES & RES_L) ? (size_t)n * KS : 0);
+  double* s_twr = reinterpret_cast<double*>(smem + SO::twr);
+  double* s_dur = reinterpret_cast<double*>(smem + SO::dur);
+  float* s_twl = reinterpret_cast<float*>(smem + SO::twl);
+  float* s_dem = reinterpret_cast<float*>(smem + SO::dem);
+  int* s_crd = reinterpret_cast<int*>(smem + SO::crd);
+  float* s_dcur = reinterpret_cast<float*>(smem + SO::dcur);
+  float* s_z = reinterpret_cast<float*>(smem + SO::z);
+  float* s_serve = reinterpret_cast<float*>(smem + SO::serve);
+  float* s_o = reinterpret_cast<float*>(smem + SO::o);
+  float* s_q = reinterpret_cast<float*>(smem + SO::qb);        // query of the current step, written by threads 128..255
+  float* s_red = reinterpret_cast<float*>(smem + SO::red);
+  uint32_t* s_mw = reinterpret_cast<uint32_t*>(smem + SO::mw);
+  uint16_t* s_idx = reinterpret_cast<uint16_t*>(smem + SO::idx);
+  double* s_fin = reinterpret_cast<double*>(smem + SO::fin);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SO::bar);
 
   // keys = [3][KB][n][128]: K', V, LK' as three plain row-major matrices (written by agh_precompute's GEMM epilogue)
   const size_t KB = a.key_mod > 0 ? (size_t)a.key_mod : (size_t)a.B;
@@ -203,8 +253,8 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     if (RES & RES_L) bulk_g2s(sL, gL, mat_bytes, bar);
     if (RES & RES_P) bulk_g2s(sP, gpsc, (uint32_t)n * D * 4, bar);
   }
-  // K' -> registers: the 16 features of head `warp` for nodes lane + 32 p (one-time global read)
-  float kreg[NPL][HD];
+  // K' -> registers: the 16 features of head `warp` for nodes lane + 32 p (one-time global read), as FFMA2 operand pairs
+  uint64_t kreg[NPL][HD / 2];
 #pragma unroll
   for (int p = 0; p < NPL; ++p) {
     const int j = lane + 32 * p;
@@ -212,7 +262,8 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     for (int i = 0; i < 4; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j < n) v = __ldg(reinterpret_cast<const float4*>(gK + (size_t)j * KS) + warp * 4 + i);
-      kreg[p][4 * i] = v.x; kreg[p][4 * i + 1] = v.y; kreg[p][4 * i + 2] = v.z; kreg[p][4 * i + 3] = v.w;
+      kreg[p][2 * i] = pack2(v.x, v.y);
+      kreg[p][2 * i + 1] = pack2(v.z, v.w);
     }
   }
   // node vectors and per-instance constants with ordinary loads while the bulk copies fly
@@ -237,8 +288,10 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   }
   __syncthreads();
   mbar_wait(bar, 0);
-  // the staged rows are plain: permute the 16-byte chunks of every aligned 8-chunk group by (node & 7) in place (swz()
-  // below), so that lanes reading the same logical chunk of 8 consecutive nodes hit 8 different bank groups
+  // the staged rows are plain: permute the 16-byte chunks of every aligned 8-chunk group by (node & 7) in place (swz()),
+  // so that lanes reading the same logical chunk of 8 consecutive nodes hit 8 different bank groups.  LK' needs it on
+  // the compact path only: the fixed logit mapping reads whole 128-byte groups of one row per quarter-warp.
+  constexpr bool SWV = (RES & RES_V) != 0, SWL = COMPACT && (RES & RES_L) != 0;     // global rows are read as they are
   {
     auto swizzle_rows = [&](float* m) {
       for (int it = tid; it < n * 4; it += 256) {
@@ -253,14 +306,13 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         for (int c = 0; c < 8; ++c) grp[((c + rot) & 7) ^ x] = tmp[c];
       }
     };
-    if (RES & RES_V) swizzle_rows(sV);
-    if (RES & RES_L) swizzle_rows(sL);
+    if (SWV) swizzle_rows(sV);
+    if (SWL) swizzle_rows(sL);
     __syncthreads();
   }
 
   const float* Vm = (RES & RES_V) ? sV : gV;
   const float* Lm = (RES & RES_L) ? sL : gL;
-  constexpr bool SWV = (RES & RES_V) != 0, SWL = (RES & RES_L) != 0;     // global rows are read as they are
   const float* Pm = (RES & RES_P) ? sP : gpsc;
 
   // ---- constants of the node(s) whose feasibility this thread evaluates (node = tid + 256 k) ----
@@ -284,7 +336,8 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   double cft = -60.0;
 
   const int h = warp;
-  const bool replay = a.mode == AGH_REPLAY;
+  const bool replay = DBG && a.mode == AGH_REPLAY;
+  const bool sampling = a.mode == AGH_SAMPLING;
   const uint64_t rng_id = (uint64_t)(a.id_offset + b);
   const size_t trow = (size_t)b * a.t_stride;
   const int nwords = (n + 31) / 32;
@@ -293,14 +346,39 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   // normal, hence temp >= 0.25); colder temperatures take the exact max-merging path
   const bool fixed_shift = a.temp >= 0.25f;
   const float shift = __fdiv_rn(10.0f, a.temp);
-  const bool tie_check = a.mode == AGH_GREEDY && a.inject_logp == nullptr;     // production greedy selection
+  const bool tie_check = a.mode == AGH_GREEDY && !(DBG && a.inject_logp != nullptr);     // production greedy selection
 
-  // (1) distance from the current location to the node(s) this thread masks, and this thread's component of the
-  //     current node's P_sc row when that table is not in shared memory: both come through L2, so they are requested
-  //     as soon as the node is known (end of the previous step) and land during the log-likelihood / state update
-  float ddm[MPT];
+  // ---- per-lane row pointers of the fixed (non-compact) value / logit mappings: every LDS.128 of the step loop is
+  //      [register + immediate].  The last 32-node pass may run past n: those lanes read a clamped (valid) row; their
+  //      softmax weight is 0 and their logit is masked.
+  //      value phase: lane <-> node lane + 32 p, chunks 4h..4h+3 of the swizzled V row;
+  //      logit phase: 4 nodes per warp and pass, 8 lanes per node; lane fg takes chunks {fg, fg+8, fg+16, fg+24} of the
+  //      plain LK' row (a quarter-warp reads 128 contiguous bytes: conflict-free) and keeps the matching chunks of o.
+  const int ns = lane >> 3, fg = lane & 7;
+  const float4* vb[4];
+  const float4* vb_last[4];
+  {
+    const int jl = min(lane + 32 * (NPL - 1), n - 1);
 #pragma unroll
-  for (int k = 0; k < MPT; ++k) ddm[k] = (tid + 256 * k < n) ? __ldg(a.distance + NODE_SIZE * s_crd[0] + cjm[k]) : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      vb[i] = reinterpret_cast<const float4*>(Vm + (size_t)lane * KS) + (SWV ? swz(h * 4 + i, lane) : h * 4 + i);
+      vb_last[i] = reinterpret_cast<const float4*>(Vm + (size_t)jl * KS) + (SWV ? swz(h * 4 + i, jl) : h * 4 + i);
+    }
+  }
+  const float4* lrow = reinterpret_cast<const float4*>(Lm + (size_t)(warp * 4 + ns) * KS) + fg;
+  const float4* lrow_last = reinterpret_cast<const float4*>(Lm + (size_t)min(32 * (NPL - 1) + warp * 4 + ns, n - 1) * KS) + fg;
+
+  // (1) distance and travel time (distance / 110 in f32, precomputed table: bit-identical to the reference's division)
+  //     from the current location to the node(s) this thread masks, and this thread's component of the current node's
+  //     P_sc row when that table is not in shared memory: all come through L2, so they are requested as soon as the node
+  //     is known (end of the previous step) and land during the log-likelihood / state update
+  float ddm[MPT], ttm[MPT];
+#pragma unroll
+  for (int k = 0; k < MPT; ++k) {
+    const bool ok = tid + 256 * k < n;
+    ddm[k] = ok ? __ldg(a.distance + NODE_SIZE * s_crd[0] + cjm[k]) : 0.f;
+    ttm[k] = ok ? __ldg(a.travel + NODE_SIZE * s_crd[0] + cjm[k]) : 0.f;
+  }
   float pv_r = 0.f;
   if (!(RES & RES_P) && qi >= 0) pv_r = __ldg(Pm + qi);
 
@@ -314,18 +392,15 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     // reads of step t (no barrier separates a step's selection phase from the next step's mask phase)
     double* fin_t = s_fin + (t & 1) * NPAD;
 
-    // (2) query for my head: attention_model.py:432-435,510-522
-    const float rem = 1.0f - used;
-    float tf;
-    {   // (float)(cft / 1440.0) with an FMA-corrected reciprocal instead of the f64 division subroutine
+    // (2) one component of the query per thread (threads 128..255), published through shared memory:
+    //     attention_model.py:432-435,510-522
+    if (qi >= 0) {
+      // (float)(cft / 1440.0) with an FMA-corrected reciprocal instead of the f64 division subroutine
       const double inv = 1.0 / 1440.0;
       const double q0 = cft * inv;
-      tf = (float)fma(fma(-q0, 1440.0, cft), inv, q0);
-    }
-    // one component of the query per thread (threads 128..255), published through shared memory
-    if (qi >= 0) {
+      const float tf = (float)fma(fma(-q0, 1440.0, cft), inv, q0);
       const float pv = (RES & RES_P) ? Pm[(size_t)prev * D + qi] : pv_r;
-      s_q[qi] = fmaf(wt_r, tf, fmaf(wc_r, rem, qb_r + pv));
+      s_q[qi] = fmaf(wt_r, tf, fmaf(wc_r, 1.0f - used, qb_r + pv));
     }
 
     // (4) feasibility of node tid (+256k): state_agh.py:148-174, exact dtypes; one node per thread, the
@@ -333,11 +408,11 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
 #pragma unroll
     for (int k = 0; k < MPT; ++k) {
       const int j = tid + 256 * k;
+      if (NPAD <= 128 && warp >= 4) break;      // warp-uniform: warps 4..7 only build the query
       bool mj = true;
       if (j < n && j >= 1) {
         const bool cap = __fadd_rn(demm[k], used) > 1.0f;
-        const float tt = __fdiv_rn(ddm[k], 110.0f);
-        const double fin = __dadd_rn(fmax(__dadd_rn(cft, (double)tt), (double)twlm[k]), durm[k]);
+        const double fin = __dadd_rn(fmax(__dadd_rn(cft, (double)ttm[k]), (double)twlm[k]), durm[k]);
         mj = vis[k] | cap | (fin > twrm[k]);
         fin_t[j] = fin;      // exactly the new cur_free_time if j is served next (state_agh.py:117-121): reused by the update
       }
@@ -376,29 +451,37 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       }
       __syncwarp();
     }
-    if (warp == 0) {
-      if (a.mask_dump != nullptr && lane < nwords) a.mask_dump[(trow + t) * nwords + lane] = pick_word<NPL>(mw, lane);
-      if (lane == 0) {
-        if (a.used_dump != nullptr) a.used_dump[trow + t] = used;
-        if (a.cft_dump != nullptr) a.cft_dump[trow + t] = cft;
+    if constexpr (DBG) {
+      if (warp == 0) {
+        if (a.mask_dump != nullptr && lane < nwords) a.mask_dump[(trow + t) * nwords + lane] = pick_word<NPL>(mw, lane);
+        if (lane == 0) {
+          if (a.used_dump != nullptr) a.used_dump[trow + t] = used;
+          if (a.cft_dump != nullptr) a.cft_dump[trow + t] = cft;
+        }
       }
     }
 
     // (3) compatibilities of my nodes with head h against the register-resident K' (which already holds the
     //     1/sqrt(16) and a log2(e), so the softmax below is exp2)
     float s[NPL];
-#pragma unroll
-    for (int p = 0; p < NPL; ++p) s[p] = 0.f;
     {
+      uint64_t sacc[NPL];
+#pragma unroll
+      for (int p = 0; p < NPL; ++p) sacc[p] = 0ull;
       const float4* q4 = reinterpret_cast<const float4*>(s_q + h * HD);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 qv = q4[i];
+        const uint64_t q01 = pack2(qv.x, qv.y), q23 = pack2(qv.z, qv.w);
 #pragma unroll
         for (int p = 0; p < NPL; ++p)
-          if (!COMPACT || mw[p] != 0xffffffffu)         // warp-uniform: a fully masked 32-node word needs no scores
-            s[p] = dot4(qv, make_float4(kreg[p][4 * i], kreg[p][4 * i + 1], kreg[p][4 * i + 2], kreg[p][4 * i + 3]), s[p]);
+          if (!COMPACT || mw[p] != 0xffffffffu) {       // warp-uniform: a fully masked 32-node word needs no scores
+            sacc[p] = fma2(kreg[p][2 * i], q01, sacc[p]);
+            sacc[p] = fma2(kreg[p][2 * i + 1], q23, sacc[p]);
+          }
       }
+#pragma unroll
+      for (int p = 0; p < NPL; ++p) s[p] = sum2(sacc[p]);
     }
 
     // (5) masked softmax over the nodes, warp-local: attention_model.py:559-565
@@ -408,13 +491,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       s[p] = ((mw[p] >> lane) & 1u) ? -CUDART_INF_F : s[p];
       mx = fmaxf(mx, s[p]);
     }
-    {   // warp max as ONE integer REDUX on the order-preserving key of the float (the map is its own inverse)
-      int key = __float_as_int(mx);
-      key ^= (key >> 31) & 0x7fffffff;
-      key = __reduce_max_sync(0xffffffffu, key);
-      key ^= (key >> 31) & 0x7fffffff;
-      mx = __int_as_float(key);
-    }
+    mx = fkey_inv(__reduce_max_sync(0xffffffffu, fkey(mx)));   // warp max as ONE integer REDUX on the order-preserving key
     float e[NPL], esum = 0.f;
 #pragma unroll
     for (int p = 0; p < NPL; ++p) {
@@ -427,9 +504,9 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
 
     // (6) o_h = sum_j a_j V_jh, butterfly transpose-reduce over the 32 lanes
     float acc[HD];
-#pragma unroll
-    for (int k = 0; k < HD; ++k) acc[k] = 0.f;
     if constexpr (COMPACT) {
+#pragma unroll
+      for (int k = 0; k < HD; ++k) acc[k] = 0.f;
       for (int c0 = 0; c0 < nfeas; c0 += 32) {          // lane <-> compact slot; masked nodes have weight 0 and are skipped
         const bool valid = c0 + lane < nfeas;
         const int j = valid ? (int)s_idx[c0 + lane] : 0;
@@ -453,21 +530,21 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         }
       }
     } else {
+      uint64_t acc2[HD / 2];
+  #pragma unroll
+      for (int k = 0; k < HD / 2; ++k) acc2[k] = 0ull;
   #pragma unroll
       for (int p = 0; p < NPL; ++p) {
-        const int j = lane + 32 * p;
-        if (j < n) {
-          const float4* vr = reinterpret_cast<const float4*>(Vm + (size_t)j * KS);
+        const uint64_t ee = pack2(e[p], e[p]);
   #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 v = vr[SWV ? swz(h * 4 + i, j) : h * 4 + i];
-            acc[4 * i + 0] = fmaf(e[p], v.x, acc[4 * i + 0]);
-            acc[4 * i + 1] = fmaf(e[p], v.y, acc[4 * i + 1]);
-            acc[4 * i + 2] = fmaf(e[p], v.z, acc[4 * i + 2]);
-            acc[4 * i + 3] = fmaf(e[p], v.w, acc[4 * i + 3]);
-          }
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = (p == NPL - 1) ? *vb_last[i] : vb[i][p * 32 * (KS / 4)];
+          acc2[2 * i] = fma2(ee, pack2(v.x, v.y), acc2[2 * i]);
+          acc2[2 * i + 1] = fma2(ee, pack2(v.z, v.w), acc2[2 * i + 1]);
         }
       }
+  #pragma unroll
+      for (int k = 0; k < HD / 2; ++k) unpack2(acc2[k], acc[2 * k], acc[2 * k + 1]);
     }
     {
       float r8[8], r4[4], r2[2], r1;
@@ -501,7 +578,6 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       // (7) logits of the FEASIBLE nodes: 4 nodes per warp and pass, 8 lanes per node.  Lane fg of a node takes the
       //     16-byte chunks {fg, fg+8, fg+16, fg+24} of its LK' row: the 8 lanes of a quarter-warp read one whole
       //     swizzled 128-byte group (conflict-free) and the matching chunks of o are a broadcast across the 4 nodes.
-      const int ns = lane >> 3, fg = lane & 7;
       // selection score as an order-preserving integer key, so the arg-max is two warp REDUX operations
       int best_key = (int)0x80000000, second_key = (int)0x80000000;
       int best_j = 0x7fffffff;
@@ -523,13 +599,13 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         u += __shfl_xor_sync(0xffffffffu, u, 4);
         if (valid && fg == 0) {
           float z = 10.0f * tanhf(u);                               // attention_model.py:580
-          if (a.inject_z != nullptr) z = __ldg(a.inject_z + (trow + t) * n + j);
+          if (DBG && a.inject_z != nullptr) z = __ldg(a.inject_z + (trow + t) * n + j);
           if (!unit_temp) z = __fdiv_rn(z, a.temp);                 // :447
           s_z[j] = z;
           float sc = z;
-          if (a.inject_logp != nullptr) {
+          if (DBG && a.inject_logp != nullptr) {
             sc = expf(__ldg(a.inject_logp + (trow + t) * n + j));   // argmax(exp(log_p)), :333,:377
-          } else if (a.mode == AGH_SAMPLING) {
+          } else if (sampling) {
             sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
           }
           if (fixed_shift) ws += expf(z - shift);
@@ -563,71 +639,89 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
           *reinterpret_cast<float4*>(s_red + warp * 4) = make_float4(ws, __int_as_float(kmax), __int_as_float(jmin), wm);
       }
     } else {
-      // (7) logits for 16 nodes per warp and pass; lanes 0-15 take features 0..63, lanes 16-31 64..127
-      const int half = lane >> 4, jj = lane & 15;
-      constexpr int NPASS = (NPL * 32 + 127) / 128;
-      float zp[NPASS];
-      // selection score as an order-preserving integer key, so the arg-max is two warp REDUX operations
-      int best_key = (int)0x80000000, second_key = (int)0x80000000;
-      int best_j = 0x7fffffff;
+      // (7) logits, fixed mapping: 4 nodes per warp and 32-node pass, 8 lanes per node (see the row pointers above)
+      constexpr int NP2 = NPL >= 3 ? 4 : NPL;        // passes padded to a power of two for the transpose-reduce
+      uint64_t o01[4], o23[4];
+      {
+        const float4* o4 = reinterpret_cast<const float4*>(s_o) + fg;
   #pragma unroll
-      for (int ps = 0; ps < NPASS; ++ps) {
-        const int j = ps * 128 + warp * 16 + jj;
-        float u = 0.f;
-        if (j < n) {
-          const float4* lr = reinterpret_cast<const float4*>(Lm + (size_t)j * KS);
-          const float4* o4 = reinterpret_cast<const float4*>(s_o + half * 64);
-          float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
-  #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            u0 = dot4(o4[i], lr[SWL ? swz(half * 16 + i, j) : half * 16 + i], u0);
-            u1 = dot4(o4[i + 1], lr[SWL ? swz(half * 16 + i + 1, j) : half * 16 + i + 1], u1);
-            u2 = dot4(o4[i + 2], lr[SWL ? swz(half * 16 + i + 2, j) : half * 16 + i + 2], u2);
-            u3 = dot4(o4[i + 3], lr[SWL ? swz(half * 16 + i + 3, j) : half * 16 + i + 3], u3);
-          }
-          u = (u0 + u1) + (u2 + u3);
-        }
-        u += __shfl_xor_sync(0xffffffffu, u, 16);
-        const bool mj = (j >= n) || ((pick_word<NPL>(mw, j >> 5) >> (j & 31)) & 1u);
-        float z = -CUDART_INF_F;
-        if (!mj) {
-          z = 10.0f * tanhf(u);                                   // attention_model.py:580
-          if (a.inject_z != nullptr) z = __ldg(a.inject_z + (trow + t) * n + j);
-          if (!unit_temp) z = __fdiv_rn(z, a.temp);               // :447
-        }
-        if (half == 0 && j < n) s_z[j] = z;
-        float sc = z;
-        if (a.inject_logp != nullptr) {
-          sc = (j < n) ? expf(__ldg(a.inject_logp + (trow + t) * n + j)) : -CUDART_INF_F;   // argmax(exp(log_p)), :333,:377
-        } else if (a.mode == AGH_SAMPLING && !mj) {
-          sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
-        }
-        zp[ps] = (half == 0) ? z : -CUDART_INF_F;
-        const int key = fkey(sc);
-        if (half == 0) {                                          // strict: first index wins ties
-          if (key > best_key) { second_key = best_key; best_key = key; best_j = j; }
-          else if (key > second_key) second_key = key;
+        for (int k = 0; k < 4; ++k) {
+          const float4 ov = o4[8 * k];
+          o01[k] = pack2(ov.x, ov.y);
+          o23[k] = pack2(ov.z, ov.w);
         }
       }
-      float wm = shift, ws = 0.f;
-      if (!fixed_shift) {
-        wm = -CUDART_INF_F;
+      float u[4] = {0.f, 0.f, 0.f, 0.f};
   #pragma unroll
-        for (int ps = 0; ps < NPASS; ++ps) wm = fmaxf(wm, zp[ps]);
+      for (int ps = 0; ps < NPL; ++ps) {
+        const float4* lr = (ps == NPL - 1) ? lrow_last : lrow + ps * 32 * (KS / 4);
+        uint64_t ua = 0ull, ub = 0ull;
+  #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 lv = lr[8 * k];
+          ua = fma2(o01[k], pack2(lv.x, lv.y), ua);
+          ub = fma2(o23[k], pack2(lv.z, lv.w), ub);
+        }
+        u[ps] = sum2(ua) + sum2(ub);
+      }
+      // transpose-reduce over the 8 lanes of a node group: lane (bit0, bit1 of fg) ends with the full dot product of
+      // the node of pass 2 bit0 + bit1; lanes fg and fg ^ 4 hold the same value
+      float uu;
+      int pass_own;
+      if constexpr (NP2 == 4) {
+        const bool b0 = fg & 1, b1 = fg & 2;
+        const float k0 = b0 ? u[2] : u[0], k1 = b0 ? u[3] : u[1], s0 = b0 ? u[0] : u[2], s1 = b0 ? u[1] : u[3];
+        const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 1), a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 1);
+        const float kk = b1 ? a1 : a0, ss = b1 ? a0 : a1;
+        uu = kk + __shfl_xor_sync(0xffffffffu, ss, 2);
+        pass_own = (b0 ? 2 : 0) + (b1 ? 1 : 0);
+      } else if constexpr (NP2 == 2) {
+        const bool b0 = fg & 1;
+        const float kk = b0 ? u[1] : u[0], ss = b0 ? u[0] : u[1];
+        uu = kk + __shfl_xor_sync(0xffffffffu, ss, 1);
+        uu += __shfl_xor_sync(0xffffffffu, uu, 2);
+        pass_own = b0 ? 1 : 0;
+      } else {
+        uu = u[0] + __shfl_xor_sync(0xffffffffu, u[0], 1);
+        uu += __shfl_xor_sync(0xffffffffu, uu, 2);
+        pass_own = 0;
+      }
+      uu += __shfl_xor_sync(0xffffffffu, uu, 4);
+      const bool owner = NP2 == 4 ? (fg & 4) == 0 : (NP2 == 2 ? (fg & 6) == 0 : fg == 0);
+      const int jloc = warp * 4 + ns;                       // bit of the node inside its 32-node word
+      const int j = pass_own * 32 + jloc;
+      const bool valid = owner && j < n;
+      const bool mj = !valid || ((pick_word<NPL>(mw, pass_own) >> jloc) & 1u);
+      float z = -CUDART_INF_F;
+      if (!mj) {
+        z = 10.0f * tanhf(uu);                                  // attention_model.py:580
+        if (DBG && a.inject_z != nullptr) z = __ldg(a.inject_z + (trow + t) * n + j);
+        if (!unit_temp) z = __fdiv_rn(z, a.temp);               // :447
+      }
+      if (valid) s_z[j] = z;
+      float sc = z;
+      if (DBG && a.inject_logp != nullptr) {
+        sc = valid ? expf(__ldg(a.inject_logp + (trow + t) * n + j)) : -CUDART_INF_F;   // argmax(exp(log_p)), :333,:377
+      } else if (sampling && !mj) {
+        sc = z + gumbel(a.seed, rng_id, (uint32_t)t, (uint32_t)j);
+      }
+      // selection score as an order-preserving integer key, so the arg-max is two warp REDUX operations
+      const int key = valid ? fkey(sc) : (int)0x80000000;
+      float wm = shift, ws;
+      if (!fixed_shift) {
+        wm = z;
   #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
       }
-  #pragma unroll
-      for (int ps = 0; ps < NPASS; ++ps) ws += (zp[ps] == -CUDART_INF_F) ? 0.f : expf(zp[ps] - wm);
+      ws = mj ? 0.f : expf(z - wm);
   #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, off);
       {
-        const int kmax = __reduce_max_sync(0xffffffffu, best_key);
-        int jmin = __reduce_min_sync(0xffffffffu, best_key == kmax ? best_j : 0x7fffffff);
+        const int kmax = __reduce_max_sync(0xffffffffu, key);
+        int jmin = __reduce_min_sync(0xffffffffu, key == kmax ? j : 0x7fffffff);     // first index wins ties
         if (tie_check) {      // does this warp hold a second logit within NEAR_TIE of its best one?
-          const int kthr = fkey(fkey_inv(kmax) - NEAR_TIE);
-          const bool mine = best_key == kmax && best_j == jmin;
-          if (__any_sync(0xffffffffu, (!mine && best_key >= kthr) || second_key >= kthr)) jmin |= 0x10000;
+          const float zthr = fkey_inv(kmax) - NEAR_TIE;
+          if (__popc(__ballot_sync(0xffffffffu, !mj && z >= zthr)) > 1) jmin |= 0x10000;
         }
         if (lane == 0)
           *reinterpret_cast<float4*>(s_red + warp * 4) = make_float4(ws, __int_as_float(kmax), __int_as_float(jmin), wm);
@@ -686,18 +780,27 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       S = __shfl_sync(0xffffffffu, part, 0);
     }
     if (replay) sel = (int)a.actions[trow + t];
-    {   // next step's distance row / P_sc component (see (1))
+    {   // next step's distance / travel-time row and P_sc component (see (1))
       const int cnext = s_crd[sel];
 #pragma unroll
-      for (int k = 0; k < MPT; ++k) ddm[k] = (tid + 256 * k < n) ? __ldg(a.distance + NODE_SIZE * cnext + cjm[k]) : 0.f;
+      for (int k = 0; k < MPT; ++k) {
+        const bool ok = tid + 256 * k < n;
+        ddm[k] = ok ? __ldg(a.distance + NODE_SIZE * cnext + cjm[k]) : 0.f;
+        ttm[k] = ok ? __ldg(a.travel + NODE_SIZE * cnext + cjm[k]) : 0.f;
+      }
       if (!(RES & RES_P) && qi >= 0) pv_r = __ldg(Pm + (size_t)sel * D + qi);
     }
-    const float g_z = s_z[sel];
-    const float logS = logf(S);
-    const float lp = (g_z - M) - logS;
-    ll += lp;
-    if (a.logp_full != nullptr) {
-      for (int j = tid; j < n; j += 256) a.logp_full[(trow + t) * n + j] = (s_z[j] - M) - logS;
+    // log-likelihood of the step (attention_model.py:238-250): only thread 0 reports it, so only warp 0 pays for the log
+    float lp = 0.f;
+    if (DBG || warp == 0) {
+      const float logS = logf(S);
+      lp = (s_z[sel] - M) - logS;
+      ll += lp;
+      if constexpr (DBG) {
+        if (a.logp_full != nullptr) {
+          for (int j = tid; j < n; j += 256) a.logp_full[(trow + t) * n + j] = (s_z[j] - M) - logS;
+        }
+      }
     }
 
     const float d = dc[sel];
@@ -717,7 +820,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
     if (tid == 0) {
       s_serve[sel] = (float)cft;
       a.pi[trow + t] = (int16_t)sel;
-      if (a.logp_sel != nullptr) a.logp_sel[trow + t] = lp;
+      if (DBG && a.logp_sel != nullptr) a.logp_sel[trow + t] = lp;
     }
     prev = sel;
     ++t;
@@ -735,19 +838,31 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
   for (int j = tid; j < n; j += 256) a.serve[(size_t)b * n + j] = s_serve[j];
   for (int k = t + tid; k < a.t_stride; k += 256) {
     a.pi[trow + k] = 0;
-    if (a.logp_sel != nullptr) a.logp_sel[trow + k] = 0.f;
+    if (DBG && a.logp_sel != nullptr) a.logp_sel[trow + k] = 0.f;
   }
 }
 
-template <int NPL, int RES>
+template <int NPL, int RES, bool DBG>
 static int launch_decode(const agh_decode_args& a, cudaStream_t st) {
   const int n = a.N + 1;
   const DecodeSmem L = decode_smem_layout(n, NPL, RES);
-  auto kern = decode_kernel<NPL, RES>;
+  static_assert(SmallOff<NPL>::mats % 128 == 0, "matrix region is 128-byte aligned");
+  if (L.V != SmallOff<NPL>::mats || L.twl != SmallOff<NPL>::twl || L.fin != SmallOff<NPL>::fin) {
+    set_error("agh_decode: shared-memory layout mismatch");
+    return AGH_E_UNSUPPORTED;
+  }
+  auto kern = decode_kernel<NPL, RES, DBG>;
   AGH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   kern<<<a.B, 256, L.total, st>>>(a);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
+}
+
+template <int NPL, int RES>
+static int launch_variant(const agh_decode_args& a, cudaStream_t st) {
+  const bool dbg = a.mode == AGH_REPLAY || a.inject_logp || a.inject_z || a.logp_sel || a.logp_full || a.mask_dump ||
+                   a.used_dump || a.cft_dump;
+  return dbg ? launch_decode<NPL, RES, true>(a, st) : launch_decode<NPL, RES, false>(a, st);
 }
 
 // Pick the residency: the candidate with the most resident CTAs per SM wins (two instances per SM hide
@@ -770,10 +885,10 @@ static int dispatch_res(const agh_decode_args& a, cudaStream_t st) {
     if (ctas > best_ctas) { best_ctas = ctas; best = cand[c]; }
   }
   switch (best) {
-    case RES_V | RES_L | RES_P: return launch_decode<NPL, RES_V | RES_L | RES_P>(a, st);
-    case RES_V | RES_L: return launch_decode<NPL, RES_V | RES_L>(a, st);
-    case RES_L: return launch_decode<NPL, RES_L>(a, st);
-    case 0: return launch_decode<NPL, 0>(a, st);
+    case RES_V | RES_L | RES_P: return launch_variant<NPL, RES_V | RES_L | RES_P>(a, st);
+    case RES_V | RES_L: return launch_variant<NPL, RES_V | RES_L>(a, st);
+    case RES_L: return launch_variant<NPL, RES_L>(a, st);
+    case 0: return launch_variant<NPL, 0>(a, st);
     default: break;
   }
   set_error("agh_decode: N=%d does not fit shared memory (%d bytes available)", a.N, max_smem);
@@ -789,7 +904,7 @@ extern "C" int agh_decode(const agh_decode_args* args, void* stream) {
   AGH_CHECK_ARG(a.B >= 0 && a.N >= 1 && a.N <= AGH_MAX_N - 1);
   if (a.B == 0) return AGH_OK;
   AGH_CHECK_ARG(a.keys && a.psc && a.qbase && a.coord && a.demand && a.tw_left && a.tw_right && a.duration);
-  AGH_CHECK_ARG(a.distance && a.wblob && a.pi && a.steps && a.ll && a.cost && a.serve);
+  AGH_CHECK_ARG(a.distance && a.travel && a.wblob && a.pi && a.steps && a.ll && a.cost && a.serve);
   AGH_CHECK_ARG(a.mode == AGH_GREEDY || a.mode == AGH_SAMPLING || a.mode == AGH_REPLAY);
   AGH_CHECK_ARG(a.mode != AGH_REPLAY || (a.actions != nullptr && a.replay_steps >= 0 && a.replay_steps <= a.t_stride));
   AGH_CHECK_ARG(a.t_stride >= 2 * a.N - 1 && a.t_stride >= 2);      // N = 1 takes two steps: the node, then the depot

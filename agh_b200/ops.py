@@ -140,6 +140,23 @@ def precompute(wblob, h, task: FleetTask):
     return keys, psc, qbase
 
 
+_travel_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def travel_table(distance: torch.Tensor) -> torch.Tensor:
+    """distance / 110 as the reference computes it (state_agh.py:118,167: an f32 IEEE division), once per table: the
+    decode kernel's mask path loads the quotient instead of dividing every step.  Computed on the CPU (correctly
+    rounded f32 division) and cached per distance tensor."""
+    key = (distance.data_ptr(), distance._version, str(distance.device))
+    t = _travel_cache.get(key)
+    if t is None:
+        if len(_travel_cache) > 16:
+            _travel_cache.clear()
+        t = (distance.detach().cpu().to(torch.float32) / 110.0).to(distance.device).contiguous()
+        _travel_cache[key] = t
+    return t
+
+
 def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.AGH_GREEDY, temp: float = 1.0,
            seed: int = 0, id_offset: int = 0, actions: Optional[torch.Tensor] = None, replay_steps: int = 0,
            reps: int = 1, inject_logp: Optional[torch.Tensor] = None, inject_z: Optional[torch.Tensor] = None,
@@ -175,6 +192,7 @@ def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.
         coord=ptr(task.coord, torch.uint8), demand=ptr(task.demand, torch.float32),
         tw_left=ptr(task.tw_left, torch.float32), tw_right=ptr(task.tw_right, torch.float64),
         duration=ptr(task.duration, torch.float64), distance=ptr(distance, torch.float32),
+        travel=ptr(travel_table(distance), torch.float32),
         wblob=ptr(wblob, torch.float32), key_mod=Bk if reps > 1 else 0, smem_mats=int(smem_mats), mode=mode, temp=float(temp),
         seed=int(seed) & (2 ** 64 - 1), id_offset=int(id_offset), actions=ptr(actions), replay_steps=int(replay_steps),
         inject_logp=ptr(inject_logp, torch.float32), inject_z=ptr(inject_z, torch.float32), t_stride=T, pi=ptr(out['pi']),

@@ -119,6 +119,8 @@ typedef struct {
   const double* tw_right;  /* [B][n] */
   const double* duration;  /* [B][n], duration[b][0] = 0 */
   const float* distance;   /* [92*92] */
+  const float* travel;     /* [92*92] travel time = distance / 110 as an f32 IEEE division (state_agh.py:118,167),
+                              precomputed once so that the mask path loads it instead of dividing every step */
   const float* wblob;      /* for w_cap / w_time */
   /* shared-key replication (sample_many, utils/functions.py:171-188): instance r of B uses the
      keys/psc/qbase/node vectors of instance r % key_mod when key_mod > 0 */

@@ -266,10 +266,12 @@ def _rollout(model, arrays, bs=1000):
     return rollout(model, ds, opts)
 
 
-# Every greedy divergence from the reference must happen at a step whose top-2 probability gap (in the reference's
-# own log-probs) is below this bound.  The kernel's log-prob error is ~1e-6, so a decision
-# whose gap exceeds 1e-5 cannot flip.
-GAP_TOL = 1e-5
+# Every greedy divergence from the reference must happen at a step whose top-2 probability gap (in the reference's own
+# log-probs) is below the fp32 noise bound.  Two fp32 evaluations of the network differ: measured on B200 at N = 100
+# (tools/diag_logp.py, profiles/r2_logp_error.md) max |log_p - float64| is 1.5e-4 for the kernel and 0.8e-4 for the
+# reference's own CPU path, kernel vs reference 1.85e-4.  A top-2 pair has p <= 0.5, so a decision can flip while the
+# probability gap is below 0.5 * 1.85e-4 = 9.2e-5; typical gaps at the observed divergences are 4e-6 .. 2e-5.
+GAP_TOL = 1e-4
 # floors for the fraction of instances whose 10 fleet costs ALL equal the reference's, and the measured rates
 # (B200, seed-4321 validation sets, random-init seed-1234 weights) are recorded in DESIGN.md section 5
 MATCH_FLOOR = {20: 0.995, 50: 0.99, 100: 0.99}
