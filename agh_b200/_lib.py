@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libagh_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['decode.cu', 'encoder.cu', 'gemm_tc.cu', 'mha_mma.cu', 'env.cu']
+SOURCES = ['decode.cu', 'encoder.cu', 'gemm_tc.cu', 'mha_mma.cu', 'env.cu', 'train.cu']
 NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17']
 
@@ -71,7 +71,21 @@ class DecodeArgs(C.Structure):
         ('t_stride', C.c_int),
         ('pi', C.c_void_p), ('steps', C.c_void_p), ('status', C.c_void_p), ('ll', C.c_void_p), ('cost', C.c_void_p), ('serve', C.c_void_p),
         ('logp_sel', C.c_void_p), ('logp_full', C.c_void_p), ('mask_dump', C.c_void_p), ('used_dump', C.c_void_p),
-        ('cft_dump', C.c_void_p), ('B', C.c_int), ('N', C.c_int),
+        ('cft_dump', C.c_void_p), ('q_dump', C.c_void_p), ('attn_dump', C.c_void_p), ('o_dump', C.c_void_p),
+        ('lse_dump', C.c_void_p), ('B', C.c_int), ('N', C.c_int),
+    ]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ('A', C.c_void_p), ('lda', C.c_longlong), ('transA', C.c_int),
+        ('B', C.c_void_p), ('ldb', C.c_longlong), ('transB', C.c_int),
+        ('C', C.c_void_p), ('ldc', C.c_longlong),
+        ('M', C.c_int), ('N', C.c_int), ('K', C.c_int), ('batch1', C.c_int), ('batch2', C.c_int),
+        ('sA1', C.c_longlong), ('sA2', C.c_longlong), ('sB1', C.c_longlong), ('sB2', C.c_longlong),
+        ('sC1', C.c_longlong), ('sC2', C.c_longlong),
+        ('alpha', C.c_float), ('accumulate', C.c_int), ('bias', C.c_void_p), ('relu', C.c_int),
+        ('mask', C.c_void_p), ('ldm', C.c_longlong), ('splits', C.c_int),
     ]
 
 
@@ -106,6 +120,17 @@ SYMBOLS = {
     'agh_state_get_mask': (_I, [C.POINTER(StateArgs), _P, _P]),
     'agh_state_update': (_I, [C.POINTER(StateArgs), _P, _P]),
     'agh_best_of': (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    'agh_sizeof_gemm_desc': (C.c_size_t, []),
+    'agh_gemm': (_I, [C.POINTER(GemmDesc), _P]),
+    'agh_gemm_f64': (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, C.c_double, _P]),
+    'agh_colsum': (_I, [_P, C.c_longlong, _I, _I, _P, _P]),
+    'agh_bn_train_fwd': (_I, [_P, _P, _P, _I, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
+    'agh_bn_train_bwd': (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    'agh_mha_fwd': (_I, [_P, _I, _I, _P, _P]),
+    'agh_mha_bwd': (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    'agh_tf_dlogits': (_I, [_P, _P, _P, _P, _P, C.c_float, _I, _I, _I, _P, _P]),
+    'agh_tf_dscore': (_I, [_P, _P, C.c_longlong, _I, _P]),
+    'agh_tf_dquery': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -452,6 +452,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       __syncwarp();
     }
     if constexpr (DBG) {
+      if (a.q_dump != nullptr && tid < D) a.q_dump[(trow + t) * D + tid] = s_q[tid];
       if (warp == 0) {
         if (a.mask_dump != nullptr && lane < nwords) a.mask_dump[(trow + t) * nwords + lane] = pick_word<NPL>(mw, lane);
         if (lane == 0) {
@@ -501,6 +502,13 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, off);
     const float inv_esum = __frcp_rn(esum);          // off the critical path of the butterfly below
+    if constexpr (DBG) {
+      if (a.attn_dump != nullptr) {
+#pragma unroll
+        for (int p = 0; p < NPL; ++p)
+          if (lane + 32 * p < n) a.attn_dump[((trow + t) * H + h) * n + lane + 32 * p] = e[p] * inv_esum;
+      }
+    }
 
     // (6) o_h = sum_j a_j V_jh, butterfly transpose-reduce over the 32 lanes
     float acc[HD];
@@ -573,6 +581,9 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       if ((lane & 1) == 0) s_o[h * HD + (lane >> 1)] = r1 * inv_esum;
     }
     __syncthreads();   // (A) o complete
+    if constexpr (DBG) {
+      if (a.o_dump != nullptr && tid < D) a.o_dump[(trow + t) * D + tid] = s_o[tid];
+    }
 
     if constexpr (COMPACT) {
       // (7) logits of the FEASIBLE nodes: 4 nodes per warp and pass, 8 lanes per node.  Lane fg of a node takes the
@@ -800,6 +811,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         if (a.logp_full != nullptr) {
           for (int j = tid; j < n; j += 256) a.logp_full[(trow + t) * n + j] = (s_z[j] - M) - logS;
         }
+        if (a.lse_dump != nullptr && tid == 0) a.lse_dump[trow + t] = M + logS;
       }
     }
 
@@ -861,7 +873,7 @@ static int launch_decode(const agh_decode_args& a, cudaStream_t st) {
 template <int NPL, int RES>
 static int launch_variant(const agh_decode_args& a, cudaStream_t st) {
   const bool dbg = a.mode == AGH_REPLAY || a.inject_logp || a.inject_z || a.logp_sel || a.logp_full || a.mask_dump ||
-                   a.used_dump || a.cft_dump;
+                   a.used_dump || a.cft_dump || a.q_dump || a.attn_dump || a.o_dump || a.lse_dump;
   return dbg ? launch_decode<NPL, RES, true>(a, st) : launch_decode<NPL, RES, false>(a, st);
 }
 

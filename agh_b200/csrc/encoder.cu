@@ -143,6 +143,21 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
         v.x = fmaf(r.x + v.x, s.x, t.x); v.y = fmaf(r.y + v.y, s.y, t.y);
         v.z = fmaf(r.z + v.z, s.z, t.z); v.w = fmaf(r.w + v.w, s.w, t.w);
       }
+      if (EPI == EPI_TRAIN) {
+        if (g.bias != nullptr) {
+          const float4 bb = *reinterpret_cast<const float4*>(g.bias + col);
+          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        }
+        if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (g.mask != nullptr) {
+          const float4 mk = *reinterpret_cast<const float4*>(g.mask + (size_t)row * g.ldm + col);
+          v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+        }
+        if (g.accumulate) {
+          const float4 c0 = *reinterpret_cast<const float4*>(g.C + (size_t)row * g.ldc + col);
+          v.x += c0.x; v.y += c0.y; v.z += c0.z; v.w += c0.w;
+        }
+      }
       if (EPI == EPI_DEC) {       // four plain [M][128] matrices: K', V, LK' (keys[0..2]) and P_sc
         float* base = col < 3 * D ? g.keys + (size_t)(col / D) * g.M * D : g.psc;
         *reinterpret_cast<float4*>(base + (size_t)row * D + col % D) = v;
@@ -168,6 +183,13 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   if (use_tensor_cores() && g.Wt != nullptr) return launch_gemm_tc<EPI>(g, st);
   dim3 grid(ceil_div(g.M, BM), g.Nc / BN);
   sgemm_kernel<EPI><<<grid, 256, 0, st>>>(g);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+int launch_sgemm_train(const GemmArgs& g, cudaStream_t st) {
+  dim3 grid(ceil_div(g.M, BM), g.Nc / BN);
+  sgemm_kernel<EPI_TRAIN><<<grid, 256, 0, st>>>(g);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
 }
@@ -316,6 +338,17 @@ extern "C" int agh_init_embed(const float* wblob, const uint8_t* coord, const fl
   const size_t total = (size_t)B * (N + 1) * (D / 4);
   init_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wblob, coord, demand, tw_left, tw_right,
                                                                                      twr_f32, B, N, h0);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+extern "C" int agh_mha_fwd(const float* qkv, int B, int N, float* heads, void* stream) {
+  AGH_CHECK_ARG(qkv && heads && B >= 0 && N >= 1 && N < AGH_MAX_N);
+  if (B == 0) return AGH_OK;
+  const int n = N + 1;
+  const size_t mha_smem = (size_t)n * 4 * HD * sizeof(float);
+  if (mha_smem > 48 * 1024) AGH_CUDA(cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mha_smem));
+  mha_kernel<<<B * (H / 2), 128, mha_smem, (cudaStream_t)stream>>>(qkv, n, heads);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
 }

@@ -203,6 +203,7 @@ extern "C" unsigned long long agh_launch_count(void) { return __atomic_load_n(&g
 extern "C" size_t agh_wblob_floats(void) { return W_TOTAL; }
 extern "C" size_t agh_sizeof_decode_args(void) { return sizeof(agh_decode_args); }
 extern "C" size_t agh_sizeof_state(void) { return sizeof(agh_state); }
+extern "C" size_t agh_sizeof_gemm_desc(void) { return sizeof(agh_gemm_desc); }
 
 extern "C" int agh_fleet_task(const int64_t* loc, const int64_t* type, const float* departure, const float* demand_all,
                               const float* tw_left_levels, int level, int fleet, const double* duration3,

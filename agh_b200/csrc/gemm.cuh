@@ -4,7 +4,7 @@
 
 namespace agh {
 
-enum { EPI_PLAIN = 0, EPI_BIAS_RELU = 1, EPI_RES_BN = 2, EPI_DEC = 3 };
+enum { EPI_PLAIN = 0, EPI_BIAS_RELU = 1, EPI_RES_BN = 2, EPI_DEC = 3, EPI_TRAIN = 4 };
 
 struct GemmArgs {
   const float* A; int lda;
@@ -20,10 +20,15 @@ struct GemmArgs {
   // tensor-core path only: C written / A read as Nc/128 (K/128) separate [M][128] matrices ("slab-major": every CTA's
   // 128 x 128 output tile is one contiguous 64 KB block) instead of one row-major [M][Nc] ([M][K]) matrix
   int c_slab, a_slab;
+  // EPI_TRAIN (training primitives, CUDA-core path only): v = acc [+ bias] [relu] [0 where mask <= 0] [+ C]
+  int relu, accumulate; const float* mask; int ldm;
 };
 
 template <int EPI>
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+
+// agh_gemm's fast path: plain row-major A [M][K] (lda) times W [K][N] (ld = N) through the tiled CUDA-core SGEMM
+int launch_sgemm_train(const GemmArgs& g, cudaStream_t st);
 
 // Self-attention of all heads on mma.sync tensor cores (mha_mma.cu): qkv [B*n][384] (or slab-major [3][B*n][128]) -> heads [B*n][128].
 int launch_mha_mma(const float* qkv, bool slab_major, int B, int n, float* heads, cudaStream_t st);

@@ -8,10 +8,10 @@ Reference call sites mirrored here (CB/nets/attention_model.py):
   _calc_log_likelihood :238-250.
 
 Eval / no-grad forward:  agh_encode -> agh_precompute -> agh_decode  (3 C-ABI calls, no host sync).
-Training forward (grad enabled): the encoder runs as a differentiable torch graph (train-mode
-BatchNorm statistics), the sampling rollout runs in agh_decode on those embeddings (no grad),
-and the log-likelihood is recomputed teacher-forced and parallel over all T steps with autograd
-(the kernel hands back the per-step masks and (used_capacity, cur_free_time) scalars).
+Training forward (grad enabled, model.train()): nets/train_fn.py -- the encoder runs through the library's training
+primitives with batch-statistics BatchNorm, the sampling rollout IS the forward pass (agh_decode returns the
+log-likelihood and records the per-step tensors), and the backward is hand-written (csrc/train.cu): no cuBLAS, SDPA or
+ATen contraction anywhere on the path.
 """
 from __future__ import annotations
 
@@ -109,6 +109,7 @@ class AttentionModel(nn.Module):
         self.id_offset = 0               # global id of instance 0 of the batch (sharding-independent sampling)
         self._blob = None
         self._blob_key = None
+        self._bn_dirty = False
         self._dist_dev = None
         self.last_steps = None           # [B] i32 steps per instance of the last rollout (device)
 
@@ -125,10 +126,19 @@ class AttentionModel(nn.Module):
         """Packed weights, re-packed whenever a parameter/buffer was modified in place or moved."""
         tensors = list(self.parameters()) + list(self.buffers())
         key = (self._device(), tuple(t._version for t in tensors), tuple(t.data_ptr() for t in tensors))
-        if self._blob is None or key != self._blob_key:
+        # the training kernels update the BatchNorm running statistics through raw pointers (no version bump): the
+        # eval-mode fold is re-packed at the first use outside training.  invalidate_blob() forces a re-pack after
+        # in-place edits through `.data`, which do not bump versions either.
+        stale_bn = self._bn_dirty and not self.training
+        if self._blob is None or key != self._blob_key or stale_bn:
+            if not self.training:
+                self._bn_dirty = False
             self._blob = pack_weights(self.state_dict(), device=self._device())
             self._blob_key = key
         return self._blob
+
+    def invalidate_blob(self):
+        self._blob = None
 
     def distance_table(self) -> torch.Tensor:
         dev = self._device()
@@ -182,25 +192,20 @@ class AttentionModel(nn.Module):
 
     # ------------------------------------------------------------------ embeddings
     def _init_embed(self, input):
-        task = self._as_task(input)
-        if torch.is_grad_enabled() and self.training:
-            return self._init_embed_torch(task)
-        return ops.init_embed(self.weight_blob(), task)
-
-    def _init_embed_torch(self, task: FleetTask):
-        """Differentiable restatement for training (attention_model.py:272-294)."""
-        x = self.loc_embedding(task.coord.long())
-        twr = task.tw_right.float() / 1440 if task.twr_f32 else (task.tw_right / 1440).float()
-        feat = torch.stack((task.demand, task.tw_left[:, 1:] / 1440, twr[:, 1:]), -1)
-        return torch.cat((x[:, :1], x[:, 1:] + self.init_embed(feat)), 1)
+        return ops.init_embed(self.weight_blob(), self._as_task(input))
 
     @_on_model_device
     def embed(self, input) -> torch.Tensor:
-        """a2+a3: node embeddings [B,n,128].  CUDA encoder in eval mode; torch graph in train mode."""
+        """a2+a3: node embeddings [B,n,128] (no grad).  Eval mode: running-statistics BatchNorm folded into the GEMM
+        epilogues; train mode: batch statistics (and the running statistics are updated, as a torch forward would)."""
         task = self._as_task(input)
-        if self.training:
-            return self.embedder(self._init_embed_torch(task))[0]
-        return ops.encode(self.weight_blob(), task)
+        with torch.no_grad():
+            if self.training:
+                from .train_fn import encoder_train_forward
+                h, _ = encoder_train_forward(self, self.weight_blob(), task, dict(self.named_parameters()),
+                                             dict(self.named_buffers()), save=False)
+                return h.view(task.B, task.N + 1, -1)
+            return ops.encode(self.weight_blob(), task)
 
     # ------------------------------------------------------------------ forward
     @_on_model_device
@@ -209,21 +214,20 @@ class AttentionModel(nn.Module):
         task = self._as_task(input)
         need_grad = torch.is_grad_enabled() and self.training
         if need_grad:
-            h = self.embed(task)
-            hd = h.detach()
+            from .train_fn import FleetTrainFn
+            named = list(self.named_parameters())
+            ll, cost, serve, pi16, steps, status = FleetTrainFn.apply(self, task, [k for k, _ in named], *[p for _, p in named])
+            out = {'pi': pi16, 'steps': steps}
         else:
             with torch.no_grad():
+                blob = self.weight_blob()
                 h = self.embed(task)
-            hd = h
-        with torch.no_grad():
-            blob = self.weight_blob()
-            keys, psc, qbase = ops.precompute(blob, hd.contiguous(), task)
-            out = ops.decode(blob, self.distance_table(), task, keys, psc, qbase, mode=self._mode(), temp=self.temp,
-                             seed=self._seed() if self.decode_type == 'sampling' else 0, id_offset=self.id_offset,
-                             want_dumps=need_grad)
+                keys, psc, qbase = ops.precompute(blob, h.contiguous(), task)
+                out = ops.decode(blob, self.distance_table(), task, keys, psc, qbase, mode=self._mode(), temp=self.temp,
+                                 seed=self._seed() if self.decode_type == 'sampling' else 0, id_offset=self.id_offset)
+            ll, cost, serve, status = out['ll'], out['cost'], out['serve'], out['status']
         self.last_steps = out['steps']
-        cost, serve = out['cost'], out['serve']
-        status = out['status']           # AGH_DECODE_STUCK: the step budget ran out with unvisited nodes
+        # status carries AGH_DECODE_STUCK: the step budget ran out with unvisited nodes
         if self.check_tours:
             # problem.get_costs' asserts (attention_model.py:183) on the zero-padded int16 tours: no host sync
             # needed for the width; the status sync happens here, or once per batch when defer_checks is set
@@ -232,51 +236,10 @@ class AttentionModel(nn.Module):
             self._pending_status.append(status.max())
         else:
             self._raise_on_status(status)
-        pi = None
-        if return_pi or need_grad:
-            T = int(out['steps'].max().item())
-            pi = out['pi'][:, :T].long()
-        ll = self._teacher_forced_ll(h, task, pi, out) if need_grad else out['ll']
         if return_pi:
-            return cost, ll, serve, pi
+            T = int(out['steps'].max().item())
+            return cost, ll, serve, out['pi'][:, :T].long()
         return cost, ll, serve
-
-    def _teacher_forced_ll(self, h, task: FleetTask, pi, out) -> torch.Tensor:
-        """Differentiable log-likelihood of the recorded actions, all T steps at once
-        (attention_model.py:429-451,510-522,550-584 with num_steps = T, then :238-250)."""
-        B, T = pi.shape
-        n = h.size(1)
-        Hh, d = self.n_heads, self.embedding_dim // self.n_heads
-        prev = torch.cat((torch.zeros_like(pi[:, :1]), pi[:, :-1]), 1)                       # [B,T]
-        used = out['used_dump'][:, :T]
-        cft = out['cft_dump'][:, :T]
-        words = out['mask_dump'][:, :T]                                                      # [B,T,W] i32
-        bits = torch.arange(32, device=h.device, dtype=torch.int32)
-        mask = ((words.unsqueeze(-1) >> bits) & 1).bool().reshape(B, T, -1)[:, :, :n]        # [B,T,n]
-        valid = torch.arange(T, device=h.device)[None, :] < out['steps'][:, None]            # [B,T]
-        mask = mask & valid[:, :, None]
-        mask[:, :, 0] = mask[:, :, 0] & valid                                                # finished rows: only depot
-        mask[:, :, 1:] = mask[:, :, 1:] | ~valid[:, :, None]
-
-        ctx = torch.cat((h.gather(1, prev[:, :, None].expand(B, T, h.size(-1))),
-                         (1.0 - used)[:, :, None], (cft / 1440).float()[:, :, None]), -1)
-        fixed = self.project_fixed_context(h.mean(1))[:, None, :]
-        fl = task.fleet_ids.long() if task.fleet_ids is not None else torch.full((B,), task.fleet, device=h.device)
-        query = fixed + self.project_step_context(ctx) + self.fleets_embedding(fl)[:, None, :]
-        gk, gv, lk = self.project_node_embeddings(h).chunk(3, dim=-1)
-        qh = query.view(B, T, Hh, d).transpose(1, 2)                                         # [B,H,T,d]
-        kh = gk.view(B, n, Hh, d).transpose(1, 2)
-        vh = gv.view(B, n, Hh, d).transpose(1, 2)
-        compat = torch.matmul(qh, kh.transpose(-2, -1)) / math.sqrt(d)                       # [B,H,T,n]
-        compat = compat.masked_fill(mask[:, None], -math.inf)
-        heads = torch.matmul(torch.softmax(compat, dim=-1), vh)                              # [B,H,T,d]
-        glimpse = self.project_out(heads.transpose(1, 2).reshape(B, T, Hh * d))
-        logits = torch.matmul(glimpse, lk.transpose(-2, -1)) / math.sqrt(glimpse.size(-1))   # [B,T,n]
-        logits = (torch.tanh(logits) * self.tanh_clipping).masked_fill(mask, -math.inf)
-        log_p = torch.log_softmax(logits / self.temp, dim=-1)
-        sel = log_p.gather(2, pi[:, :, None]).squeeze(-1)
-        assert (sel > -1000).all(), 'Logprobs should not be -inf, check sampling procedure!'
-        return (sel * valid).sum(1)
 
     # ------------------------------------------------------------------ reference-internal API kept for callers
     @_on_model_device

@@ -2,18 +2,19 @@
 (graph_encoder.py:18-207): `layers.L.0.module.{W_query,W_key,W_val,W_out}`, `layers.L.{1,3}.normalizer.*`,
 `layers.L.2.module.{0,2}.{weight,bias}`.
 
-The eval-mode forward pass does NOT run here: AttentionModel packs these parameters into the weight
-blob and calls the CUDA encoder (agh_encode).  The torch forward below exists for the differentiable
-training pass only (train-mode BatchNorm with batch statistics + autograd through cuBLAS/SDPA),
-see DESIGN.md "training".
+No forward pass runs here: AttentionModel packs these parameters into the weight blob and calls the CUDA encoder
+(agh_encode in eval mode; the training primitives of csrc/train.cu with batch-statistics BatchNorm and a hand-written
+backward in train mode, nets/train_fn.py).  The modules exist so that `state_dict()` / `load_state_dict()` /
+`parameters()` / pickling behave exactly like the reference's.
 """
 from __future__ import annotations
 
 import math
 
 import torch
-import torch.nn.functional as F
 from torch import nn
+
+_NO_FORWARD = 'parameter container only: the encoder runs inside libagh_b200 (AttentionModel.embed / forward)'
 
 
 class SkipConnection(nn.Module):
@@ -22,7 +23,7 @@ class SkipConnection(nn.Module):
         self.module = module
 
     def forward(self, x):
-        return x + self.module(x)
+        raise RuntimeError(_NO_FORWARD)
 
 
 class MultiHeadAttention(nn.Module):
@@ -42,12 +43,7 @@ class MultiHeadAttention(nn.Module):
             p.data.uniform_(-bound, bound)
 
     def forward(self, x):
-        # x [B,n,D] -> per-head projections [B,H,n,d]; softmax(QK^T/sqrt(d)) V; concat heads; W_out
-        q = torch.einsum('bnc,hck->bhnk', x, self.W_query)
-        k = torch.einsum('bnc,hck->bhnk', x, self.W_key)
-        v = torch.einsum('bnc,hck->bhnk', x, self.W_val)
-        o = F.scaled_dot_product_attention(q, k, v)               # default scale 1/sqrt(d)
-        return torch.einsum('bhnk,hkc->bnc', o, self.W_out)
+        raise RuntimeError(_NO_FORWARD)
 
 
 class Normalization(nn.Module):
@@ -58,7 +54,7 @@ class Normalization(nn.Module):
         self.normalizer = nn.BatchNorm1d(embed_dim, affine=True)
 
     def forward(self, x):
-        return self.normalizer(x.reshape(-1, x.size(-1))).view_as(x)
+        raise RuntimeError(_NO_FORWARD)
 
 
 class MultiHeadAttentionLayer(nn.Sequential):
@@ -80,6 +76,4 @@ class GraphAttentionEncoder(nn.Module):
                                       for _ in range(n_layers)])
 
     def forward(self, x, mask=None):
-        assert mask is None
-        h = self.layers(x)
-        return h, h.mean(dim=1)
+        raise RuntimeError(_NO_FORWARD)

@@ -27,6 +27,54 @@ def blob_floats() -> int:
     return 92 * D + 3 * D + D + LAYERS * layer + D * 4 * D + D * D + 10 * D + 2 * D + tc
 
 
+def offsets() -> Dict[str, int]:
+    """Float offsets of the blob sections (mirror of agh_b200/csrc/common.cuh); per-layer sections are relative to
+    'layer0' + l * 'layer_size'."""
+    o = {'loc_emb': 0}
+    o['init_w'] = o['loc_emb'] + 92 * D
+    o['init_b'] = o['init_w'] + 3 * D
+    o['layer0'] = o['init_b'] + D
+    l = {'wqkv': 0}
+    l['wo'] = l['wqkv'] + D * 3 * D
+    l['bn1s'] = l['wo'] + D * D
+    l['bn1t'] = l['bn1s'] + D
+    l['w1t'] = l['bn1t'] + D
+    l['b1'] = l['w1t'] + D * FF
+    l['w2t'] = l['b1'] + FF
+    l['b2'] = l['w2t'] + FF * D
+    l['bn2s'] = l['b2'] + D
+    l['bn2t'] = l['bn2s'] + D
+    o['layer_size'] = l['bn2t'] + D
+    o.update({'l_' + k: v for k, v in l.items()})
+    o['wdec'] = o['layer0'] + LAYERS * o['layer_size']
+    o['wfc_t'] = o['wdec'] + D * 4 * D
+    o['fleet'] = o['wfc_t'] + D * D
+    o['w_cap'] = o['fleet'] + 10 * D
+    o['w_time'] = o['w_cap'] + D
+    # K-major ([out][in]) copies: per layer wqkv^T [384][128] | wo^T [128][128] | w1 [512][128] | w2 [128][512]; then wdec^T
+    o['tc0'] = o['w_time'] + D
+    o['t_wqkv'] = 0
+    o['t_wo'] = o['t_wqkv'] + 3 * D * D
+    o['t_w1'] = o['t_wo'] + D * D
+    o['t_w2'] = o['t_w1'] + FF * D
+    o['t_size'] = o['t_w2'] + D * FF
+    o['tc_dec'] = o['tc0'] + LAYERS * o['t_size']
+    return o
+
+
+def _matmul_f64(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a @ b in float64.  On the GPU through the library's own kernel (agh_gemm_f64): the product path launches no
+    cuBLAS kernel, not even for this 128^3 fold; on the CPU (host-logic tests) plain torch."""
+    if not a.is_cuda:
+        return a @ b
+    from .. import _lib
+    a, b = a.contiguous(), b.contiguous()
+    c = torch.empty(a.size(0), b.size(1), dtype=torch.float64, device=a.device)
+    _lib.check(_lib.lib().agh_gemm_f64(a.data_ptr(), a.size(1), 0, b.data_ptr(), b.size(1), 0, c.data_ptr(), c.size(1),
+                                       a.size(0), b.size(1), a.size(1), 1.0, _lib.stream_ptr(a.device)))
+    return c
+
+
 def pack_weights(sd: Dict[str, torch.Tensor], device=None) -> torch.Tensor:
     g = lambda k: sd[k].detach().to(device=device, dtype=torch.float64)
     parts = [g('loc_embedding.weight'), g('init_embed.weight').t(), g('init_embed.bias')]
@@ -48,7 +96,7 @@ def pack_weights(sd: Dict[str, torch.Tensor], device=None) -> torch.Tensor:
     wn = g('project_node_embeddings.weight')                 # [384][128]
     wout = g('project_out.weight')                           # [128][128]  glimpse = W_out o
     wsc = g('project_step_context.weight')                   # [128][130]
-    lk_fold = (wout.t() @ wn[2 * D:3 * D]) / math.sqrt(D)    # [c][e]
+    lk_fold = _matmul_f64(wout.t(), wn[2 * D:3 * D]) / math.sqrt(D)    # [c][e]
     # K' carries 1/sqrt(16) and log2(e): the glimpse softmax runs in base 2 (exp2) in the kernel
     wdec = torch.cat((wn[0:D].t() * (math.log2(math.e) / math.sqrt(D // H)), wn[D:2 * D].t(), lk_fold.t(), wsc[:, :D].t()), 1)   # [128][512]
     parts += [wdec, g('project_fixed_context.weight').t(), g('fleets_embedding.weight'), wsc[:, D], wsc[:, D + 1]]

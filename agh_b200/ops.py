@@ -6,6 +6,7 @@ current CUDA stream.  CPU tensors are rejected (agh_b200._lib.ptr raises): no fa
 from __future__ import annotations
 
 import ctypes as C
+import ctypes as _ct
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -161,8 +162,8 @@ def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.
            seed: int = 0, id_offset: int = 0, actions: Optional[torch.Tensor] = None, replay_steps: int = 0,
            reps: int = 1, inject_logp: Optional[torch.Tensor] = None, inject_z: Optional[torch.Tensor] = None,
            want_logp_sel: bool = False,
-           want_logp_full: bool = False, want_dumps: bool = False, t_stride: Optional[int] = None,
-           smem_mats: int = 0):
+           want_logp_full: bool = False, want_dumps: bool = False, want_train_dumps: bool = False,
+           t_stride: Optional[int] = None, smem_mats: int = 0):
     """a5-a12 + a14.  `reps` > 1 runs reps*B rollouts sharing the B key sets (sample_many)."""
     Bk, N = task.B, task.N
     n = N + 1
@@ -185,6 +186,11 @@ def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.
         out['mask_dump'] = torch.zeros(B, T, (n + 31) // 32, dtype=torch.int32, device=dev)
         out['used_dump'] = torch.zeros(B, T, dtype=torch.float32, device=dev)
         out['cft_dump'] = torch.zeros(B, T, dtype=torch.float64, device=dev)
+    if want_train_dumps:       # what the REINFORCE backward differentiates (nets/train_fn.py)
+        out['q_dump'] = torch.zeros(B, T, D, dtype=torch.float32, device=dev)
+        out['attn_dump'] = torch.zeros(B, T, 8, n, dtype=torch.float32, device=dev)
+        out['o_dump'] = torch.zeros(B, T, D, dtype=torch.float32, device=dev)
+        out['lse_dump'] = torch.zeros(B, T, dtype=torch.float32, device=dev)
     if actions is not None:
         assert actions.dtype == torch.int16 and actions.shape == (B, T), (actions.dtype, actions.shape, (B, T))
     a = _lib.DecodeArgs(
@@ -199,7 +205,8 @@ def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.
         steps=ptr(out['steps']), status=ptr(out['status']), ll=ptr(out['ll']),
         cost=ptr(out['cost']), serve=ptr(out['serve']), logp_sel=ptr(out.get('logp_sel')),
         logp_full=ptr(out.get('logp_full')), mask_dump=ptr(out.get('mask_dump')), used_dump=ptr(out.get('used_dump')),
-        cft_dump=ptr(out.get('cft_dump')), B=B, N=N)
+        cft_dump=ptr(out.get('cft_dump')), q_dump=ptr(out.get('q_dump')), attn_dump=ptr(out.get('attn_dump')),
+        o_dump=ptr(out.get('o_dump')), lse_dump=ptr(out.get('lse_dump')), B=B, N=N)
     check(lib().agh_decode(C.byref(a), stream_ptr(dev)))
     return out
 
@@ -228,3 +235,91 @@ def best_of(costs, pi, serve, R: int, B: int):
     check(lib().agh_best_of(ptr(costs, torch.float32), ptr(pi, torch.int16), ptr(serve, torch.float32), R, B, n - 1, T,
                             ptr(bc), ptr(bp), ptr(bs), ptr(br), stream_ptr(dev)))
     return bc, bp, bs, br
+
+
+# ------------------------------------------------------------------------------------------------
+# a18: REINFORCE training primitives (csrc/train.cu)
+# ------------------------------------------------------------------------------------------------
+def _vptr(t: torch.Tensor, dtype=torch.float32) -> int:
+    """Device pointer of a CUDA tensor VIEW (strides are described by the caller's ld / stride arguments)."""
+    if not t.is_cuda:
+        raise _lib.AghError('agh_b200 kernels need CUDA tensors; there is no CPU path')
+    if t.dtype != dtype:
+        raise _lib.AghError('expected dtype %s, got %s' % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def gemm(A, B, C, M, N, K, lda, ldb, ldc, transA=False, transB=False, alpha=1.0, accumulate=False, bias=None, relu=False,
+         mask=None, ldm=0, splits=1, batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0)):
+    """C = alpha op(A) op(B) [+ bias] [relu] [masked] [+ C]; op(A) is M x K, op(B) is K x N (see include/agh_b200.h)."""
+    d = _lib.GemmDesc(A=_vptr(A), lda=lda, transA=int(transA), B=_vptr(B), ldb=ldb, transB=int(transB), C=_vptr(C), ldc=ldc,
+                      M=M, N=N, K=K, batch1=batch[0], batch2=batch[1], sA1=sA[0], sA2=sA[1], sB1=sB[0], sB2=sB[1],
+                      sC1=sC[0], sC2=sC[1], alpha=float(alpha), accumulate=int(accumulate),
+                      bias=None if bias is None else _vptr(bias), relu=int(relu),
+                      mask=None if mask is None else _vptr(mask), ldm=ldm, splits=splits)
+    check(lib().agh_gemm(_ct.byref(d), stream_ptr(C.device)))
+    return C
+
+
+def colsum(X, M, N, ld=None, out=None):
+    out = torch.zeros(N, dtype=torch.float32, device=X.device) if out is None else out
+    check(lib().agh_colsum(_vptr(X), N if ld is None else ld, M, N, _vptr(out), stream_ptr(X.device)))
+    return out
+
+
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, scratch, eps=1e-5, momentum=0.1):
+    M = x.numel() // D
+    y = torch.empty_like(x)
+    mean = torch.empty(D, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(D, dtype=torch.float32, device=x.device)
+    check(lib().agh_bn_train_fwd(ptr(x, torch.float32), ptr(gamma, torch.float32), ptr(beta, torch.float32), M, eps, momentum,
+                                 ptr(y), ptr(mean), ptr(rstd), ptr(running_mean, torch.float32), ptr(running_var, torch.float32),
+                                 ptr(scratch, torch.float64), stream_ptr(x.device)))
+    return y, mean, rstd
+
+
+def bn_train_bwd(dy, x, mean, rstd, gamma, scratch):
+    M = x.numel() // D
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
+    check(lib().agh_bn_train_bwd(ptr(dy, torch.float32), ptr(x, torch.float32), ptr(mean), ptr(rstd), ptr(gamma, torch.float32), M,
+                                 ptr(dx), ptr(dgamma), ptr(dbeta), ptr(scratch, torch.float64), stream_ptr(x.device)))
+    return dx, dgamma, dbeta
+
+
+def mha_fwd(qkv, B, N):
+    heads = torch.empty(B * (N + 1), D, dtype=torch.float32, device=qkv.device)
+    check(lib().agh_mha_fwd(ptr(qkv, torch.float32), B, N, ptr(heads), stream_ptr(qkv.device)))
+    return heads
+
+
+def mha_bwd(qkv, heads, dheads, B, N):
+    dqkv = torch.empty_like(qkv)
+    check(lib().agh_mha_bwd(ptr(qkv, torch.float32), ptr(heads, torch.float32), ptr(dheads, torch.float32), B, N, ptr(dqkv),
+                            stream_ptr(qkv.device)))
+    return dqkv
+
+
+def tf_dlogits(logp_full, lse, pi, steps, grad_ll, temp, N):
+    B, T, n = logp_full.shape
+    dU = torch.empty_like(logp_full)
+    check(lib().agh_tf_dlogits(ptr(logp_full, torch.float32), ptr(lse, torch.float32), ptr(pi, torch.int16), ptr(steps, torch.int32),
+                               ptr(grad_ll, torch.float32), float(temp), B, T, N, ptr(dU), stream_ptr(dU.device)))
+    return dU
+
+
+def tf_dscore_(attn, dattn, N):
+    rows = attn.numel() // (N + 1)
+    check(lib().agh_tf_dscore(ptr(attn, torch.float32), ptr(dattn, torch.float32), rows, N, stream_ptr(attn.device)))
+    return dattn
+
+
+def tf_dquery(dQ, pi, steps, used, cft, N, dwcap, dwtime):
+    B, T, _ = dQ.shape
+    dqbase = torch.empty(B, D, dtype=torch.float32, device=dQ.device)
+    dpsc = torch.zeros(B, N + 1, D, dtype=torch.float32, device=dQ.device)
+    check(lib().agh_tf_dquery(ptr(dQ, torch.float32), ptr(pi, torch.int16), ptr(steps, torch.int32), ptr(used, torch.float32),
+                              ptr(cft, torch.float64), B, T, N, ptr(dqbase), ptr(dpsc), ptr(dwcap, torch.float32),
+                              ptr(dwtime, torch.float32), stream_ptr(dQ.device)))
+    return dqbase, dpsc

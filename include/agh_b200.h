@@ -148,6 +148,12 @@ typedef struct {
   uint32_t* mask_dump;     /* optional [B][t_stride][ceil(n/32)], bit=1 infeasible */
   float* used_dump;        /* optional [B][t_stride] used capacity before the step */
   double* cft_dump;        /* optional [B][t_stride] cur_free_time before the step */
+  /* optional per-step tensors the REINFORCE backward differentiates (attention_model.py:510-584 with num_steps = T):
+     the step's query, the glimpse attention weights, the glimpse and the log-sum-exp of the masked logits */
+  float* q_dump;           /* [B][t_stride][128] */
+  float* attn_dump;        /* [B][t_stride][8][n] */
+  float* o_dump;           /* [B][t_stride][128] */
+  float* lse_dump;         /* [B][t_stride]: log_p_j = logit_j / temp - lse */
   int B, N;
 } agh_decode_args;
 
@@ -178,6 +184,50 @@ typedef struct {
 size_t agh_sizeof_state(void);
 int agh_state_get_mask(const agh_state* st, uint8_t* mask /*[B][n], 1 = infeasible*/, void* stream);
 int agh_state_update(const agh_state* st, const int64_t* selected /*[B]*/, void* stream);
+
+/* ---- a18: REINFORCE training primitives (train.py:159-219; graph_encoder.py:56-172 and attention_model.py:392-451,
+ *      510-584 differentiated).  agh_b200/nets/train_fn.py composes them into the forward / backward of one fleet. ---- */
+/* generic fp32 GEMM  C = alpha op(A) op(B) [+ bias[n]] [relu] [zeroed where mask <= 0] [+ C]
+ *   op(A) is M x K: element (m,k) = transA ? A[k*lda + m] : A[m*lda + k];   op(B) is K x N: (k,n) = transB ? B[n*ldb + k] : B[k*ldb + n]
+ *   batched over (b1, b2) with independent element strides; splits > 1 = split-K with atomic accumulation into C
+ *   (C must hold the value to accumulate onto; bias / relu / mask are not allowed then) */
+typedef struct {
+  const float* A; long long lda; int transA;
+  const float* B; long long ldb; int transB;
+  float* C; long long ldc;
+  int M, N, K;
+  int batch1, batch2;
+  long long sA1, sA2, sB1, sB2, sC1, sC2;
+  float alpha;
+  int accumulate;
+  const float* bias;
+  int relu;
+  const float* mask; long long ldm;
+  int splits;
+} agh_gemm_desc;
+size_t agh_sizeof_gemm_desc(void);
+int agh_gemm(const agh_gemm_desc* desc, void* stream);
+/* float64 product for the weight packing (nets/weights.py: project_out folded into the logit keys) */
+int agh_gemm_f64(const double* A, int lda, int transA, const double* B, int ldb, int transB, double* C, int ldc,
+                 int M, int N, int K, double alpha, void* stream);
+/* out[n] += sum_m X[m*ld + n] (bias gradients) */
+int agh_colsum(const float* X, long long ld, int M, int N, float* out, void* stream);
+/* BatchNorm1d(128) in training mode over M rows (graph_encoder.py:137-138): y, batch mean / rstd (for the backward), running
+ * statistics updated in place when non-NULL; scratch: 256 doubles */
+int agh_bn_train_fwd(const float* x, const float* gamma, const float* beta, int M, float eps, float momentum, float* y,
+                     float* mean, float* rstd, float* running_mean, float* running_var, double* scratch, void* stream);
+int agh_bn_train_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
+                     float* dx, float* dgamma, float* dbeta, double* scratch, void* stream);
+/* encoder self-attention (graph_encoder.py:83-104) on row-major qkv [B*n][384] -> heads [B*n][128], and its backward */
+int agh_mha_fwd(const float* qkv, int B, int N, float* heads, void* stream);
+int agh_mha_bwd(const float* qkv, const float* heads, const float* dheads, int B, int N, float* dqkv, void* stream);
+/* decoder backward, element-wise pieces: logit gradient from the recorded log-probs; dS' of the base-2 glimpse softmax
+ * (in place on dattn); fan-out of the query gradient to qbase / P_sc rows / capacity and time columns */
+int agh_tf_dlogits(const float* logp_full, const float* lse, const int16_t* pi, const int32_t* steps, const float* grad_ll,
+                   float temp, int B, int T, int N, float* dU, void* stream);
+int agh_tf_dscore(const float* attn, float* dattn, long long rows, int N, void* stream);
+int agh_tf_dquery(const float* dQ, const int16_t* pi, const int32_t* steps, const float* used, const double* cft, int B,
+                  int T, int N, float* dqbase, float* dpsc, float* dwcap, float* dwtime, void* stream);
 
 /* ---- a16: best-of-R reduction of sample_many (utils/functions.py:190-223) -------------------
  *   costs[R*B] (replica-major: row r*B+b), pi[R*B][t_stride] i16, serve[R*B][n]

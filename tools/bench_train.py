@@ -51,20 +51,26 @@ def main():
     sync(); t1 = time.perf_counter()
     model.train()
     nb = 0
+    per_batch = []
     for bid, batch in enumerate(iter_batches(training, args.batch_size)):
         if ws > 1:
             lo, hi = parallel.shard_bounds(batch['baseline'].size(0), rank, ws)
             batch = {'data': {k: v[lo:hi] for k, v in batch['data'].items()}, 'baseline': batch['baseline'][lo:hi]}
+        tb = time.perf_counter()
         train_batch_agh(model, optimizer, baseline, 0, bid, bid + 1, batch, None, opts)
+        sync()
+        per_batch.append(time.perf_counter() - tb)
         nb += 1
     sync(); t2 = time.perf_counter()
+    steady = sorted(per_batch[2:])[len(per_batch[2:]) // 2] if len(per_batch) > 4 else (t2 - t1) / nb     # median after warm-up
     validate(model, val, opts)
     sync(); t3 = time.perf_counter()
     if rank == 0:
         print(json.dumps({'config': 'C4 AGH-%d REINFORCE' % args.flights, 'n_gpus': ws, 'epoch_size': args.epoch_size,
                           'batch_size': args.batch_size, 'baseline_wrap_s': t1 - t0, 'train_s': t2 - t1,
-                          'ms_per_train_batch': 1e3 * (t2 - t1) / nb, 'validate_s': t3 - t2,
-                          'projected_epoch_12800_s': (t1 - t0) * 12800 / args.epoch_size + (t2 - t1) * 200 / nb + (t3 - t2)}))
+                          'ms_per_train_batch': 1e3 * steady, 'ms_per_train_batch_incl_warmup': 1e3 * (t2 - t1) / nb,
+                          'validate_s': t3 - t2,
+                          'projected_epoch_12800_s': (t1 - t0) * 12800 / args.epoch_size + steady * 12800 / args.batch_size + (t3 - t2)}))
     if ws > 1:
         dist.destroy_process_group()
 
