@@ -120,6 +120,7 @@ SYMBOLS = {
     'agh_state_get_mask': (_I, [C.POINTER(StateArgs), _P, _P]),
     'agh_state_update': (_I, [C.POINTER(StateArgs), _P, _P]),
     'agh_best_of': (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    'agh_generate': (_I, [C.c_uint64, C.c_longlong, _I, _I, _I, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
     'agh_sizeof_gemm_desc': (C.c_size_t, []),
     'agh_gemm': (_I, [C.POINTER(GemmDesc), _P]),
     'agh_gemm_f64': (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, C.c_double, _P]),

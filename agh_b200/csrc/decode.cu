@@ -365,8 +365,7 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       vb_last[i] = reinterpret_cast<const float4*>(Vm + (size_t)jl * KS) + (SWV ? swz(h * 4 + i, jl) : h * 4 + i);
     }
   }
-  const float4* lrow = reinterpret_cast<const float4*>(Lm + (size_t)(warp * 4 + ns) * KS) + fg;
-  const float4* lrow_last = reinterpret_cast<const float4*>(Lm + (size_t)min(32 * (NPL - 1) + warp * 4 + ns, n - 1) * KS) + fg;
+  const float4* lbase = reinterpret_cast<const float4*>(Lm) + fg;
 
   // (1) distance and travel time (distance / 110 in f32, precomputed table: bit-identical to the reference's division)
   //     from the current location to the node(s) this thread masks, and this thread's component of the current node's
@@ -450,6 +449,25 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         if (j < n && ((pick_word<NPL>(mw, warp + 8 * k) >> lane) & 1u)) s_z[j] = -CUDART_INF_F;
       }
       __syncwarp();
+    } else {
+      // N <= 127: the LOGIT phase walks a compact list of the step's feasible nodes (about 30 % of them on average), which
+      // cuts its shared-memory wavefronts -- the busiest unit of this kernel (profiles/r2c_decode_ncu_summary.md) -- to the
+      // rows that matter.  Warp p builds the entries of its own 32-node word while the other phases of the step run; the
+      // list is complete at barrier (A).  Increasing slot = increasing node index (first-index tie-break).
+      int before = 0;
+  #pragma unroll
+      for (int p = 0; p < NPL; ++p) {
+        const int c = __popc(~mw[p]);
+        before += (p < warp) ? c : 0;
+        nfeas += c;
+      }
+      if (warp < NPL) {
+        const uint32_t fw = ~pick_word<NPL>(mw, warp);
+        if ((fw >> lane) & 1u) s_idx[before + __popc(fw & ((1u << lane) - 1u))] = (uint16_t)(32 * warp + lane);
+      }
+      if constexpr (DBG) {     // the full log-prob output wants -inf at the masked nodes
+        if (tid < n && ((pick_word<NPL>(mw, warp) >> lane) & 1u)) s_z[tid] = -CUDART_INF_F;
+      }
     }
     if constexpr (DBG) {
       if (a.q_dump != nullptr && tid < D) a.q_dump[(trow + t) * D + tid] = s_q[tid];
@@ -663,17 +681,22 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
         }
       }
       float u[4] = {0.f, 0.f, 0.f, 0.f};
+      int jn[4] = {0, 0, 0, 0};
   #pragma unroll
       for (int ps = 0; ps < NPL; ++ps) {
-        const float4* lr = (ps == NPL - 1) ? lrow_last : lrow + ps * 32 * (KS / 4);
-        uint64_t ua = 0ull, ub = 0ull;
+        if (ps * 32 < nfeas) {                                  // warp-uniform: passes beyond the list are skipped
+          const int c = ps * 32 + warp * 4 + ns;
+          jn[ps] = c < nfeas ? (int)s_idx[c] : 0;               // lanes past the end read row 0 (their result is dropped)
+          const float4* lr = lbase + jn[ps] * (KS / 4);
+          uint64_t ua = 0ull, ub = 0ull;
   #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4 lv = lr[8 * k];
-          ua = fma2(o01[k], pack2(lv.x, lv.y), ua);
-          ub = fma2(o23[k], pack2(lv.z, lv.w), ub);
+          for (int k = 0; k < 4; ++k) {
+            const float4 lv = lr[8 * k];
+            ua = fma2(o01[k], pack2(lv.x, lv.y), ua);
+            ub = fma2(o23[k], pack2(lv.z, lv.w), ub);
+          }
+          u[ps] = sum2(ua) + sum2(ub);
         }
-        u[ps] = sum2(ua) + sum2(ub);
       }
       // transpose-reduce over the 8 lanes of a node group: lane (bit0, bit1 of fg) ends with the full dot product of
       // the node of pass 2 bit0 + bit1; lanes fg and fg ^ 4 hold the same value
@@ -699,10 +722,9 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
       }
       uu += __shfl_xor_sync(0xffffffffu, uu, 4);
       const bool owner = NP2 == 4 ? (fg & 4) == 0 : (NP2 == 2 ? (fg & 6) == 0 : fg == 0);
-      const int jloc = warp * 4 + ns;                       // bit of the node inside its 32-node word
-      const int j = pass_own * 32 + jloc;
-      const bool valid = owner && j < n;
-      const bool mj = !valid || ((pick_word<NPL>(mw, pass_own) >> jloc) & 1u);
+      const int j = pass_own == 0 ? jn[0] : (pass_own == 1 ? jn[1] : (pass_own == 2 ? jn[2] : jn[3]));
+      const bool valid = owner && pass_own * 32 + warp * 4 + ns < nfeas;      // every list entry is a feasible node
+      const bool mj = !valid;
       float z = -CUDART_INF_F;
       if (!mj) {
         z = 10.0f * tanhf(uu);                                  // attention_model.py:580
@@ -759,15 +781,13 @@ __global__ void __launch_bounds__(256, decode_min_blocks(NPL)) decode_kernel(con
           // re-decide with the reference's arithmetic: log_p = (z - max) - log(sum exp(z - max)), p = exp(log_p),
           // first index of the maximum (attention_model.py:446-447,333,377).  Every warp computes the same values.
           float ssum = 0.f;
-          for (int j = lane; j < n; j += 32) {
-            const float z = s_z[j];
-            ssum += (z == -CUDART_INF_F) ? 0.f : expf(z - zmax);
-          }
+          for (int c = lane; c < nfeas; c += 32) ssum += expf(s_z[s_idx[c]] - zmax);     // the list holds the feasible nodes
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, off);
           const float lse = logf(ssum);
           int pk = (int)0x80000000, pj = 0x7fffffff;
-          for (int j = lane; j < n; j += 32) {
+          for (int c = lane; c < nfeas; c += 32) {                    // increasing slot = increasing node index
+            const int j = s_idx[c];
             const float z = s_z[j];
             if (z >= zmax - NEAR_TIE) {
               const int k2 = __float_as_int(expf((z - zmax) - lse));      // p > 0: its bits order like the value

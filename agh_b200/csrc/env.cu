@@ -56,6 +56,52 @@ __global__ void chain_kernel(float* __restrict__ lvl, const float* __restrict__ 
   lvl[idx] = fmaxf(lvl[idx], serve[b * (N + 1) + j + 1]);
 }
 
+// ---- instance generator on the device (problem_agh.py:93-116 / generate_data.py:8-18 semantics) ----
+// One thread per (instance, flight); Philox4x32-10 keyed by the seed, counter = (instance, flight, draw block).  Same
+// distributions as the reference's numpy draws -- loc ~ U{1..91}, arrival = 60 Cat(arrival_prob) + U{0..59},
+// type ~ U{0,1,2}, departure = arrival + (30,34,33)[type], demand ~ U{1..9} / capacity -- but NOT the same stream:
+// the numpy generator (problems/agh/problem_agh.py) stays the parity generator.
+__device__ __forceinline__ void philox4(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ uint32_t bounded(uint32_t r, uint32_t n) { return __umulhi(r, n); }      // floor(r n / 2^32) in [0, n)
+
+__global__ void generate_kernel(uint64_t seed, long long id_offset, int B, int N, int fleets, float capacity,
+                                const float* __restrict__ arrival_cdf /*[24], cdf[23] = 1*/, int64_t* __restrict__ loc,
+                                float* __restrict__ arrival, float* __restrict__ departure, int64_t* __restrict__ type,
+                                float* __restrict__ demand /*[B][fleets][N]*/) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * N) return;
+  const size_t b = idx / N;
+  const int j = (int)(idx % N);
+  const uint64_t gid = (uint64_t)(id_offset + (long long)b);
+  uint32_t r[4];
+  philox4(seed, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)j, 0u, r);
+  loc[idx] = 1 + (int64_t)bounded(r[0], 91u);
+  const float u = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  int hour = 0;
+  while (hour < 23 && u > arrival_cdf[hour]) ++hour;
+  const float arr = (float)(60 * hour + (int)bounded(r[2], 60u));
+  const int ty = (int)bounded(r[3], 3u);
+  arrival[idx] = arr;
+  type[idx] = ty;
+  departure[idx] = arr + (ty == 0 ? 30.0f : (ty == 1 ? 34.0f : 33.0f));
+  for (int f0 = 0; f0 < fleets; f0 += 4) {
+    philox4(seed, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)j, 1u + (uint32_t)(f0 >> 2), r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (f0 + k < fleets) demand[(b * fleets + f0 + k) * N + j] = __fdiv_rn((float)(1 + bounded(r[k], 9u)), capacity);
+  }
+}
+
 // ---- a13: problem_agh.py:18-66, one warp per instance ----
 template <typename PiT>
 __global__ void get_costs_kernel(const PiT* __restrict__ pi, int T, const uint8_t* __restrict__ coord,
@@ -274,6 +320,17 @@ extern "C" int agh_best_of(const float* costs, const int16_t* pi, const float* s
   if (B == 0) return AGH_OK;
   best_of_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(costs, pi, serve, R, B, N + 1, t_stride, best_cost, best_pi, best_serve,
                                                       best_rep);
+  AGH_LAUNCH_CHECK();
+  return AGH_OK;
+}
+
+extern "C" int agh_generate(uint64_t seed, long long id_offset, int B, int N, int fleets, float capacity, const float* arrival_cdf,
+                            int64_t* loc, float* arrival, float* departure, int64_t* type, float* demand, void* stream) {
+  AGH_CHECK_ARG(arrival_cdf && loc && arrival && departure && type && demand && B >= 0 && N >= 1 && fleets >= 1 && capacity > 0.f);
+  if (B == 0) return AGH_OK;
+  const size_t total = (size_t)B * N;
+  generate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, id_offset, B, N, fleets, capacity,
+                                                                                   arrival_cdf, loc, arrival, departure, type, demand);
   AGH_LAUNCH_CHECK();
   return AGH_OK;
 }

@@ -53,6 +53,7 @@ _FLAGS = [
     ('fine_tune', 'flag', False, 'accepted'),
     ('wo_time', 'flag', False, 'ablation, out of scope'),
     ('rnn_time', 'flag', False, 'ablation, out of scope'),
+    ('device_data', 'flag', False, "generate each epoch's training instances on the GPU (Philox stream, not the numpy one)"),
 ]
 
 

@@ -65,13 +65,41 @@ def generate_arrays(num_samples, size, fleet_size=10, rng=np.random):
             'demand': torch.from_numpy(demand).to(torch.float32)}
 
 
+def generate_arrays_device(num_samples, size, device, seed=None, fleet_size=10, id_offset=0):
+    """The same distributions drawn ON THE DEVICE by one kernel (agh_generate: Philox4x32-10 keyed by seed, instance id
+    and flight): a 12,800-instance epoch set without the host numpy pass and the H2D copy.  NOT bit-compatible with the
+    reference's numpy stream -- generate_arrays stays the parity generator.  `seed` defaults to a draw from torch's CPU
+    generator, so datasets are reproducible under torch.manual_seed and identical on every rank."""
+    device = torch.device(device)
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    cdf = torch.from_numpy(np.cumsum(np.load(_TABLES)['arrival_prob']).astype(np.float32))
+    cdf[-1] = 1.0
+    cdf = cdf.to(device)
+    out = {'loc': torch.empty(num_samples, size, dtype=torch.int64, device=device),
+           'arrival': torch.empty(num_samples, size, dtype=torch.float32, device=device),
+           'departure': torch.empty(num_samples, size, dtype=torch.float32, device=device),
+           'type': torch.empty(num_samples, size, dtype=torch.int64, device=device),
+           'demand': torch.empty(num_samples, fleet_size, size, dtype=torch.float32, device=device)}
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().agh_generate(seed & (2 ** 64 - 1), int(id_offset), num_samples, size, fleet_size, float(CAPACITIES[size]),
+                                           _lib.ptr(cdf), _lib.ptr(out['loc']), _lib.ptr(out['arrival']), _lib.ptr(out['departure']),
+                                           _lib.ptr(out['type']), _lib.ptr(out['demand']), _lib.stream_ptr(device)))
+    return out
+
+
 class AGHDataset(Dataset):
     """Items are dicts {'loc' i64 [N], 'arrival' f32 [N], 'departure' f32 [N], 'type' i64 [N], 'demand' f32 [10,N]}.
     Storage is one tensor per field (`self.arrays`) so whole batches can be sliced without collation."""
 
-    def __init__(self, filename=None, size=50, num_samples=1000000, offset=0, distribution=None, fleet_size=10):
+    def __init__(self, filename=None, size=50, num_samples=1000000, offset=0, distribution=None, fleet_size=10,
+                 device=None, seed=None):
+        """device: a CUDA device generates the instances there (generate_arrays_device; not the numpy stream); the
+        default (None) is the reference's host generator, draw for draw."""
         super().__init__()
-        if filename is not None:
+        if filename is None and device is not None and torch.device(device).type == 'cuda':
+            self.arrays = generate_arrays_device(num_samples, size, device, seed=seed, fleet_size=fleet_size, id_offset=offset)
+        elif filename is not None:
             assert os.path.splitext(filename)[1] == '.pkl'
             with open(filename, 'rb') as f:
                 data = pickle.load(f)[offset:offset + num_samples]

@@ -139,8 +139,12 @@ def train_epoch(model, optimizer, baseline, lr_scheduler, epoch, val_dataset, pr
     if not opts.no_tensorboard and tb_logger is not None:
         tb_logger.log_value('learnrate_pg0', optimizer.param_groups[0]['lr'], step)
 
+    # --device_data: the epoch's instances are generated on the GPU (one kernel, no host pass / H2D copy; Philox stream,
+    # not the reference's numpy stream)
+    gen_dev = opts.device if getattr(opts, 'device_data', False) else None
     training_dataset = baseline.wrap_dataset(
-        problem.make_dataset(size=opts.graph_size, num_samples=opts.epoch_size, distribution=opts.data_distribution))
+        problem.make_dataset(size=opts.graph_size, num_samples=opts.epoch_size, distribution=opts.data_distribution,
+                             **({'device': gen_dev} if gen_dev is not None else {})))
     model.train()
     set_decode_type(model, 'sampling')
     rank, ws = parallel.world()

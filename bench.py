@@ -343,6 +343,175 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+def _dist_setup():
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', 0))
+    ws = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU path'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if ws > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    return dist, rank, ws, local, dev, barrier
+
+
+def run_strong(args):
+    """--scaling strong (BASELINE.json configs[2] read literally: ONE batch of 10,000 AGH-100 instances sharded over the
+    ranks).  A step = train.rollout(model, dataset, opts): every rank copies its contiguous shard to the device, solves the
+    10 fleets (same-level fleets batched into one launch sequence while a shard is below 16 k instance-fleets, which
+    keeps the CTA waves full at 1,250 instances per rank), and the [B/G,10] cost table is all-gathered over NCCL (C2) --
+    the collective is inside the timed region.  value = the device-resident variant (shard already in HBM), e2e = with
+    the pinned-host copy and the D2H of the gathered table."""
+    from agh_b200 import AttentionModel, AGH, AGHDataset, _lib, parallel
+    from agh_b200.train import rollout, fleet_rollout
+    dist, rank, ws, local, dev, barrier = _dist_setup()
+    N, B = args.flights, args.batch
+    torch.manual_seed(1234)
+    model = AttentionModel(128, 128, AGH).to(dev)
+    model.eval(); model.set_decode_type('greedy')
+    host = {k: v.pin_memory() for k, v in make_batch(B, N, 4321).items()}       # the same batch on every rank
+    ds = AGHDataset.__new__(AGHDataset)
+    torch.utils.data.Dataset.__init__(ds)
+    ds.arrays, ds.size = host, B
+    lo, hi = parallel.shard_bounds(B, rank, ws)
+    shard = {k: v[lo:hi].to(dev) for k, v in host.items()}
+    opts = types.SimpleNamespace(eval_batch_size=B, device=dev, no_progress_bar=True)
+    lib = _lib.lib()
+
+    def step_resident():
+        with torch.no_grad():
+            costs, _ = fleet_rollout(model, shard, dev)
+        model.raise_pending()
+        return parallel.all_gather_rows(costs, B)
+
+    model.defer_checks = True
+    for _ in range(args.warmup):
+        step_resident(); rollout(model, ds, opts)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = lib.agh_launch_count()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    barrier(); e[0].record()
+    for _ in range(args.steps):
+        table = step_resident()
+    e[1].record(); barrier()
+    launches = (lib.agh_launch_count() - l0) // args.steps
+    barrier(); e[2].record()
+    for _ in range(args.steps):
+        host_costs = rollout(model, ds, opts)
+    e[3].record(); barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e[0].elapsed_time(e[1]) / args.steps, e[2].elapsed_time(e[3]) / args.steps], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_res, ms_e2e = t.tolist()
+    if rank == 0:
+        h2d = sum(v[lo:hi].numel() * v.element_size() for v in host.values())
+        print(json.dumps({
+            'metric': METRIC, 'value': B / (ms_res * 1e-3), 'unit': UNIT, 'n_gpus': ws, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'AGH-%d greedy rollout, ONE batch of %d instances sharded over %d rank(s), 10 fleets (configs[2])' % (N, B, ws),
+                       'flights': N, 'global_batch': B, 'per_gpu_batch': hi - lo,
+                       'parallelism': 'contiguous instance shards; all-gather of the [B/G,10] cost table (NCCL) inside the timed region',
+                       'l2': 'inputs larger than L2 (keys %.2f GB per rank and fleet vs 126 MB L2)' % ((hi - lo) * 3 * (N + 1) * 512 / 1e9)},
+            'clocks': clocks,
+            'e2e': {'value': B / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': B * 10 * 4,
+                    'ms_per_step': ms_e2e, 'api': 'agh_b200.train.rollout(model, dataset, opts) under torch.distributed'},
+            'gpu_launches': int(launches), 'avg_cost': float(host_costs.sum(1).mean()),
+            'checksum_rank0_equals_gather': bool(torch.equal(table.cpu(), host_costs))}))
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def run_train(args):
+    """--workload train (BASELINE.json configs[3]): REINFORCE steps on a GLOBAL batch sharded over the ranks; one flat
+    all-reduce of the 705,408 gradients (+ BatchNorm buffers) per step over NCCL (C1) inside the timed region.  A step =
+    train.train_batch_agh: 10 sampling rollouts with the recorded per-step tensors, hand-written backward, all-reduce,
+    clip, Adam.  Reports ms per global batch, instances/s and the projected 12,800-instance epoch."""
+    from agh_b200 import AttentionModel, AGH, AGHDataset, _lib, parallel
+    from agh_b200.train import train_batch_agh, rollout
+    dist, rank, ws, local, dev, barrier = _dist_setup()
+    N, G = args.flights, args.train_batch
+    torch.manual_seed(1234)
+    model = AttentionModel(128, 128, AGH).to(dev)
+    optimizer = torch.optim.Adam([{'params': model.parameters(), 'lr': 1e-4}])
+    data = make_batch(G, N, 4321)
+    ds = AGHDataset.__new__(AGHDataset)
+    torch.utils.data.Dataset.__init__(ds)
+    ds.arrays, ds.size = data, G
+    opts = types.SimpleNamespace(eval_batch_size=1000, device=dev, no_progress_bar=True, max_grad_norm=1.0, log_step=1e9,
+                                 no_tensorboard=True, baseline='rollout')
+    bl = rollout(model, ds, opts)                                  # greedy baseline values [G,10] (sharded + gathered)
+    lo, hi = parallel.shard_bounds(G, rank, ws)
+    batch = {'data': {k: v[lo:hi] for k, v in data.items()}, 'baseline': bl[lo:hi]}
+    baseline = types.SimpleNamespace(unwrap_batch=lambda b: (b['data'], b['baseline']))
+    lib = _lib.lib()
+    model.train()
+    for i in range(args.warmup):
+        train_batch_agh(model, optimizer, baseline, 0, i, i + 1, batch, None, opts)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = lib.agh_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); e0.record()
+    for i in range(args.steps):
+        train_batch_agh(model, optimizer, baseline, 0, i, i + 1, batch, None, opts)
+    e1.record(); barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (lib.agh_launch_count() - l0) // args.steps
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    # all ranks hold identical weights after the all-reduced steps
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()] + [b.detach().float().reshape(-1) for b in model.buffers()])
+    same = True
+    if ws > 1:
+        ref = flat.clone(); dist.broadcast(ref, 0)
+        ok = torch.tensor([float(torch.equal(ref, flat))], device=dev); dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        same = bool(ok.item())
+    if rank == 0:
+        line = {'metric': 'agh%d_reinforce_train_instances_per_sec' % N, 'value': G / (ms * 1e-3), 'unit': UNIT, 'n_gpus': ws,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'AGH-%d REINFORCE step (sampling rollouts of 10 fleets + backward + Adam), global batch %d '
+                                       'sharded over %d rank(s) (configs[3])' % (N, G, ws), 'flights': N, 'global_batch': G,
+                           'per_gpu_batch': hi - lo,
+                           'parallelism': 'DDP-style: one flat all-reduce(avg) of 705,408 f32 gradients + BatchNorm buffers per step (NCCL)'},
+                'clocks': clocks, 'gpu_launches': int(launches), 'ranks_hold_identical_weights': same,
+                'projected_epoch_12800_s': 12800 / G * ms * 1e-3}
+        if ws == 1 and not args.no_cpu_baseline:
+            from oracle import agh_oracle as O
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+            tb, W = O.Tables.load(), O.random_init_weights(1234)
+            Bc = 16
+            inst = {k: v[:Bc].clone() for k, v in data.items()}
+            t0 = time.perf_counter()
+            col = []
+            torch.manual_seed(0)
+            O.rollout(W, tb, inst, mode='sampling', collect=col)
+            Wg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in W.items()}
+            loss, _ = O.reinforce_loss(Wg, tb, inst, bl[:Bc], [c['pi'] for c in col])
+            loss.backward()
+            dt = time.perf_counter() - t0
+            line['cpu_baseline'] = {'value': Bc / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                                    'sample': '%d instances: sampling rollout + REINFORCE loss + backward of the oracle port, %.1f s' % (Bc, dt)}
+        print(json.dumps(line))
+    if ws > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -354,6 +523,10 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=256, help='--impl reference: instances per step')
     ap.add_argument('--cpu-baseline-sample', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak (default, the headline): --batch instances per GPU; strong: ONE batch of --batch instances sharded over the ranks')
+    ap.add_argument('--workload', default='rollout', choices=['rollout', 'train'])
+    ap.add_argument('--train-batch', type=int, default=512, help='--workload train: global batch')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == 'reference':
@@ -361,7 +534,12 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3
-        run_cuda(args)
+        if args.workload == 'train':
+            run_train(args)
+        elif args.scaling == 'strong':
+            run_strong(args)
+        else:
+            run_cuda(args)
 
 
 if __name__ == '__main__':

@@ -161,6 +161,12 @@ int agh_decode(const agh_decode_args* args, void* stream);
 /* ABI guard for FFI bindings: sizeof(agh_decode_args) as compiled */
 size_t agh_sizeof_decode_args(void);
 
+/* ---- f3: instance generation on the device (problem_agh.py:93-116, generate_data.py:8-18): the reference's
+ *      distributions from a Philox4x32-10 stream keyed by (seed, instance id, flight) -- not the numpy stream.
+ *   arrival_cdf[24]: cumulative arrival-hour probabilities.  demand is [B][fleets][N]. */
+int agh_generate(uint64_t seed, long long id_offset, int B, int N, int fleets, float capacity, const float* arrival_cdf,
+                 int64_t* loc, float* arrival, float* departure, int64_t* type, float* demand, void* stream);
+
 /* ---- a13: tour validation + cost (problem_agh.py:18-66) ------------------------------------
  *   pi[B][T] i64 or i16.  cost[B] f32, status[B] i32 (0 = valid; AGH_TOUR_INVALID | ... otherwise).
  */

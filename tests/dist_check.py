@@ -53,6 +53,10 @@ def main():
     ref = flat.clone()
     dist.broadcast(ref, 0)
     assert torch.equal(flat, ref), 'parameters diverged across ranks after the all-reduced step'
+    bufs = torch.cat([b.detach().float().reshape(-1) for b in model.buffers()])
+    ref = bufs.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(bufs, ref), 'BatchNorm running statistics diverged across ranks (they are averaged with the gradients)'
 
     # sharding-independent sampling: rank r samples its slice with global ids; compare with rank 0 doing all of it
     model.eval()
@@ -65,11 +69,13 @@ def main():
                           lv, 0, 1, info['duration'][1], info['next_duration'][0], False)
     model.id_offset = 0
     with torch.no_grad():
+        model.sampling_seed = 99            # (re)setting the seed restarts its per-rollout counter
         c_full = model(full)[0]
         xs = {k: v[lo:hi].contiguous() for k, v in x.items()}
         part = ops.fleet_task(xs['loc'], xs['type'], xs['departure'], xs['demand'], xs['arrival'].repeat(6, 1, 1).contiguous(),
                               0, 1, info['duration'][1], info['next_duration'][0], False)
         model.id_offset = lo
+        model.sampling_seed = 99
         c_part = model(part)[0]
     assert torch.equal(c_part, c_full[lo:hi]), 'sampled tours depend on the sharding'
     dist.barrier()

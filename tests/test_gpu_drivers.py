@@ -243,3 +243,54 @@ def test_resume_from_reference_checkpoint(tmp_path, weights):
     optimizer = torch.optim.Adam([{'params': model.parameters(), 'lr': 1e-4}])
     optimizer.load_state_dict(ck['optimizer'])
     torch.set_rng_state(ck['rng_state'])
+
+
+def test_multi_gpu_dist_check():
+    """(e): tests/dist_check.py under torchrun on 2 GPUs (NCCL): sharded rollout == single-rank rollout, parameters and
+    BatchNorm buffers identical on all ranks after an all-reduced training step, sampled tours independent of the
+    sharding.  Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                          '127.0.0.1', '--master-port', '29541', os.path.join(root, 'tests', 'dist_check.py')],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and 'dist_check OK' in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+def test_device_side_dataset_generation(cuda_model):
+    """f3: AGH.make_dataset(..., device='cuda') draws the reference's distributions (problem_agh.py:93-116) on the GPU:
+    ranges, arrival-hour marginal, type / demand / gate frequencies, determinism per seed, and the instances roll out."""
+    from agh_b200 import AGH
+    from agh_b200.problems.agh.problem_agh import CAPACITIES
+    torch.manual_seed(3)
+    ds = AGH.make_dataset(size=100, num_samples=4000, device='cuda')
+    a = ds.arrays
+    assert all(v.is_cuda for v in a.values()) and len(ds) == 4000
+    assert a['loc'].dtype == torch.int64 and a['type'].dtype == torch.int64 and a['demand'].shape == (4000, 10, 100)
+    assert int(a['loc'].min()) == 1 and int(a['loc'].max()) == 91 and int(a['type'].min()) == 0 and int(a['type'].max()) == 2
+    stay = torch.tensor([30., 34., 33.], device='cuda')[a['type']]
+    assert torch.equal(a['departure'], a['arrival'] + stay)
+    units = a['demand'] * CAPACITIES[100]
+    assert torch.allclose(units, units.round(), atol=1e-4) and int(units.round().min()) == 1 and int(units.round().max()) == 9
+    prob = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'agh_b200', 'problems', 'agh', 'agh_tables.npz'))['arrival_prob']
+    hours = torch.bincount((a['arrival'] // 60).long().view(-1), minlength=24).cpu().numpy() / a['arrival'].numel()
+    assert np.abs(hours - prob).max() < 4e-3                                  # 400,000 draws
+    minutes = torch.bincount((a['arrival'] % 60).long().view(-1), minlength=60).float() / a['arrival'].numel()
+    assert (minutes - 1 / 60).abs().max() < 2e-3
+    gates = torch.bincount(a['loc'].view(-1), minlength=92)[1:].float() / a['loc'].numel()
+    assert (gates - 1 / 91).abs().max() < 2e-3
+    assert abs(units.mean().item() - 5.0) < 0.02
+    torch.manual_seed(3)
+    again = AGH.make_dataset(size=100, num_samples=4000, device='cuda')
+    assert all(torch.equal(again.arrays[k], a[k]) for k in a)
+    other = AGH.make_dataset(size=100, num_samples=4000, device='cuda')
+    assert not torch.equal(other.arrays['loc'], a['loc'])
+    item = ds[5]
+    assert item['demand'].shape == (10, 100) and item['loc'].shape == (100,)
+    from agh_b200.train import rollout
+    costs = rollout(cuda_model, AGH.make_dataset(size=50, num_samples=96, device='cuda'),
+                    types.SimpleNamespace(eval_batch_size=64, device=torch.device('cuda'), no_progress_bar=True))
+    assert costs.shape == (96, 10) and torch.isfinite(costs).all()
