@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libagh_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['decode.cu', 'encoder.cu', 'gemm_tc.cu', 'mha_mma.cu', 'env.cu', 'train.cu']
+SOURCES = ['decode.cu', 'decode_shared.cu', 'encoder.cu', 'gemm_tc.cu', 'mha_mma.cu', 'env.cu', 'train.cu']
 NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17']
 

@@ -927,6 +927,8 @@ static int dispatch_res(const agh_decode_args& a, cudaStream_t st) {
   return AGH_E_UNSUPPORTED;
 }
 
+int try_decode_shared(const agh_decode_args& a, cudaStream_t st, bool* taken);      // decode_shared.cu
+
 }  // namespace agh
 
 extern "C" int agh_decode(const agh_decode_args* args, void* stream) {
@@ -942,6 +944,11 @@ extern "C" int agh_decode(const agh_decode_args* args, void* stream) {
   AGH_CHECK_ARG(a.t_stride >= 2 * a.N - 1 && a.t_stride >= 2);      // N = 1 takes two steps: the node, then the depot
   AGH_CHECK_ARG(a.temp > 0.f);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {   // replicas that share one staged key set (sample_many): one warp per replica, decode_shared.cu
+    bool taken = false;
+    const int rc = try_decode_shared(a, st, &taken);
+    if (rc != AGH_OK || taken) return rc;
+  }
   const int npl = ceil_div(a.N + 1, 32);
   switch (npl) {
     case 1: return dispatch_res<1>(a, st);

@@ -163,8 +163,12 @@ def decode(wblob, distance, task: FleetTask, keys, psc, qbase, mode: int = _lib.
            reps: int = 1, inject_logp: Optional[torch.Tensor] = None, inject_z: Optional[torch.Tensor] = None,
            want_logp_sel: bool = False,
            want_logp_full: bool = False, want_dumps: bool = False, want_train_dumps: bool = False,
-           t_stride: Optional[int] = None, smem_mats: int = 0):
-    """a5-a12 + a14.  `reps` > 1 runs reps*B rollouts sharing the B key sets (sample_many)."""
+           t_stride: Optional[int] = None, smem_mats: int = 0, shared_keys: bool = True):
+    """a5-a12 + a14.  `reps` > 1 runs reps*B rollouts sharing the B key sets (sample_many): in sampling mode they take
+    the shared-key kernel (one staged key set per CTA, one warp per replica; csrc/decode_shared.cu) unless
+    shared_keys=False forces one CTA per replica."""
+    if not shared_keys:
+        smem_mats = int(smem_mats) | 64
     Bk, N = task.B, task.N
     n = N + 1
     B = Bk * reps

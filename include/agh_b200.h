@@ -125,7 +125,8 @@ typedef struct {
   /* shared-key replication (sample_many, utils/functions.py:171-188): instance r of B uses the
      keys/psc/qbase/node vectors of instance r % key_mod when key_mod > 0 */
   int key_mod;
-  int smem_mats;           /* shared-memory residency: 0 = auto; else 8 | bitmask (1: V, 2: LK', 4: P_sc); the rest is read via L2 */
+  int smem_mats;           /* shared-memory residency: 0 = auto; else 8 | bitmask (1: V, 2: LK', 4: P_sc); the rest is read via L2.
+                              Bit 64: never take the shared-key kernel (one warp per replica, used for key_mod > 0 sampling) */
   int mode;                /* AGH_GREEDY | AGH_SAMPLING | AGH_REPLAY */
   float temp;              /* softmax temperature (attention_model.py:447) */
   uint64_t seed;           /* Philox key; counter = (instance id, step, node) */

@@ -479,6 +479,46 @@ def test_sample_many_best_of(cuda_model, tables):
         cuda_model.set_decode_type('greedy')
 
 
+@pytest.mark.parametrize('n,B,R', [(20, 3, 200), (50, 2, 1280), (100, 2, 37)])
+def test_shared_key_sampling_kernel(cuda_model, tables, weights, n, B, R):
+    """f1: the shared-key kernel (one staged key set per CTA, one warp per replica; csrc/decode_shared.cu) draws the SAME
+    Philox noise as the per-instance kernel: with the same seed nearly every replica samples the identical tour (the two
+    kernels sum their dot products in different orders, so a Gumbel arg-max can flip at a near-tie); every tour is valid
+    and its cost equals the validator's; replayed through the CPU oracle the serve times are exact and ll agrees to 1e-4."""
+    from agh_b200 import ops, _lib
+    inst = {k: v[:B] for k, v in make_instances(n).items()}
+    task_cpu = O.fleet_task(tables, inst, 3, O.new_tw_left_levels(inst))
+    task = to_task(task_cpu)
+    shared = cuda_forward(cuda_model, task, mode=_lib.AGH_SAMPLING, seed=77, reps=R)
+    single = cuda_forward(cuda_model, task, mode=_lib.AGH_SAMPLING, seed=77, reps=R, shared_keys=False)
+    same = (shared['pi'] == single['pi']).all(1)
+    assert same.float().mean().item() > 0.97, same.float().mean().item()
+    assert torch.allclose(shared['ll'][same], single['ll'][same], rtol=LOGP_RTOL, atol=1e-4)
+    assert torch.equal(shared['cost'][same], single['cost'][same]) and torch.equal(shared['serve'][same], single['serve'][same])
+    assert torch.equal(shared['steps'][same], single['steps'][same]) and int(shared['status'].max()) == 0
+    # validity + cost through the validator (replica-major rows: row r*B + b uses instance b)
+    from agh_b200.ops import FleetTask
+    rep = lambda v: v.repeat(R, *([1] * (v.dim() - 1))).contiguous()
+    big = FleetTask(rep(task.coord), rep(task.demand), rep(task.tw_left), rep(task.tw_right), rep(task.duration), task.twr_f32, task.fleet,
+                    None if task.fleet_ids is None else rep(task.fleet_ids))
+    cost, status = ops.get_costs(shared['pi'], big, cuda_model.distance_table())
+    assert int(status.max()) == 0 and torch.equal(cost, shared['cost'])
+    # replay 48 sampled rollouts through the oracle
+    G = min(48, R * B)
+    rows = torch.arange(G)
+    T = int(shared['steps'][:G].max())
+    task_r = {k: torch.stack([v[int(r) % B] for r in rows]) for k, v in task_cpu.items()}
+    with torch.no_grad():
+        h = O.encoder(weights, O.init_embed(weights, task_r))
+        rp = O.decode(weights, task_r, h, mode='replay', actions=shared['pi'][:G, :T].cpu().long())
+    assert np.array_equal(shared['serve'][:G].cpu().numpy(), rp['serve'].numpy())
+    assert np.allclose(shared['ll'][:G].cpu().numpy(), rp['ll'].numpy(), rtol=LOGP_RTOL, atol=2e-4)
+    assert np.allclose(shared['cost'][:G].cpu().numpy(), O.get_costs(task_r, rp['pi']).numpy(), rtol=COST_RTOL)
+    # different seeds, different tours; ragged replica count (R not a multiple of the warps per CTA) covered by R = 37 / 200
+    other = cuda_forward(cuda_model, task, mode=_lib.AGH_SAMPLING, seed=78, reps=R)
+    assert not torch.equal(other['pi'], shared['pi'])
+
+
 @pytest.mark.parametrize('n,B', [(300, 4), (100, 2048)])
 def test_large_sizes_properties(cuda_model, tables, weights, n, B):
     """Sizes beyond the golden fixtures: tours are valid under the reference's own asserts, steps are in
