@@ -284,10 +284,24 @@ def run_cuda(args):
         enc_tflops = f_enc_flops(N) * B * 10 / ((t_enc + t_pre) * 1e-3) / 1e12
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         # physical DRAM bytes per decode launch from the committed `ncu --set full` capture of this very workload
-        traffic = None
-        tp = os.path.join(ROOT, 'profiles', 'r1f_decode_traffic.json')
+        # (ncu cannot run inside a timed benchmark: the figure is the committed capture of this round's kernel, refreshed
+        # whenever the kernel changes; profiles/r2c_decode_ncu_summary.md)
+        traffic, onchip = None, None
+        tp = os.path.join(ROOT, 'profiles', 'r2c_decode_traffic.json')
         if os.path.exists(tp) and (N, B) == (100, 10000):
-            traffic = json.load(open(tp))['traffic_bytes_per_launch']
+            prof = json.load(open(tp))
+            traffic = prof['traffic_bytes_per_launch']
+            # honest on-chip view: the matrices never leave the SM, so the step is bounded by shared-memory wavefronts and
+            # FMA issue, not by HBM.  Floors per instance-step: V + LK' rows read once (2 n 512 B / 128 B per wavefront),
+            # 3 n 128 MACs on 128 FMA lanes per SM; measured = SM-clocks per instance-step from this run's launch time.
+            clk = 1.965e9
+            per_step_clk = dec_launch_ms * 1e-3 * clk * 148 / inst_steps_per_launch
+            smem_floor, fma_floor = 2 * n * 512 / 128.0, 3 * n * 128 / 128.0
+            onchip = {'clk_per_instance_step_per_sm': per_step_clk, 'smem_floor_clk': smem_floor, 'fma_floor_clk': fma_floor,
+                      'frac_of_smem_floor': smem_floor / per_step_clk, 'frac_of_fma_floor': fma_floor / per_step_clk,
+                      'ncu_this_round': {k: prof[k] for k in ('issue_active_pct', 'smem_pipe_pct_of_peak', 'fma_pipe_pct', 'alu_pipe_pct')},
+                      'note': 'latency-bound: three block barriers and the serial select/update per step; '
+                              'profiles/r2c_decode_ncu_summary.md'}
         line = {
             'metric': METRIC, 'value': B * ws / (ms_res * 1e-3), 'unit': UNIT, 'n_gpus': ws, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -311,7 +325,8 @@ def run_cuda(args):
                          'instance_steps_per_launch': inst_steps_per_launch, 'launch_ms': dec_launch_ms,
                          'share_of_step': t_dec / ms_res,
                          'note': 'keys stay on chip (registers + shared memory) for all T steps, so the fraction exceeds 1: '
-                                 'physical DRAM traffic is the one-time staging only (profiles/r1f_decode_traffic.json)'},
+                                 'physical DRAM traffic is the one-time staging only (profiles/r2c_decode_traffic.json); see roofline_onchip'},
+            'roofline_onchip': onchip,
             'roofline_encoder': {'kernels': 'gemm_tc_kernel + mha_mma_kernel + init_embed (agh_encode, agh_precompute)',
                                  'bound': 'tensor', 'achieved': enc_tflops, 'peak': tflops, 'unit': 'TFLOP/s',
                                  'frac': enc_tflops / tflops, 'share_of_step': (t_enc + t_pre) / ms_res,
