@@ -58,39 +58,45 @@ __global__ void init_embed_kernel(const float* __restrict__ w, const uint8_t* __
 // ------------------------------------------------------------------------------------------
 // SGEMM  C[M,Nc] = epi(A[M,K] @ W[K,Nc])
 // ------------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 128, BK = 16, LDA_S = BM + 4;
+constexpr int BM = 128, BN = 128, BK = 16;
 
-template <int EPI>
+// BMT: rows per CTA tile: 128 (8 x 8 outputs per thread; the 10^6-row evaluation GEMMs) or 64 (4 x 8; the 6,464-row training
+// GEMMs with 128 output columns, which would otherwise launch 51 CTAs on 148 SMs)
+template <int EPI, int BMT = 128>
 __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
-  __shared__ __align__(16) float As[2][BK][LDA_S];
+  constexpr int RH = BMT / 64;                              // row halves of 64 per tile; thread rows: 4 per half
+  constexpr int TR = 4 * RH;
+  __shared__ __align__(16) float As[2][BK][BMT + 4];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.x * BMT, n0 = blockIdx.y * BN;
 
   // global -> register staging
-  const int a_row = tid >> 2, a_k = (tid & 3) * 4;          // rows a_row, a_row+64
+  const int a_row = tid >> 2, a_k = (tid & 3) * 4;          // rows a_row (, a_row+64)
   const int b_k = tid >> 5, b_n = (tid & 31) * 4;           // k rows b_k, b_k+8
-  float4 ra[2], rb[2];
+  float4 ra[RH], rb[2];
   auto load_tiles = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < RH; ++i) {
       const int r = m0 + a_row + 64 * i;
       ra[i] = (r < g.M) ? *reinterpret_cast<const float4*>(g.A + (size_t)r * g.lda + k0 + a_k) : make_float4(0.f, 0.f, 0.f, 0.f);
-      rb[i] = *reinterpret_cast<const float4*>(g.W + (size_t)(k0 + b_k + 8 * i) * g.Nc + n0 + b_n);
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) rb[i] = *reinterpret_cast<const float4*>(g.W + (size_t)(k0 + b_k + 8 * i) * g.Nc + n0 + b_n);
   };
   auto store_tiles = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < RH; ++i) {
       const int r = a_row + 64 * i;
       As[buf][a_k + 0][r] = ra[i].x; As[buf][a_k + 1][r] = ra[i].y; As[buf][a_k + 2][r] = ra[i].z; As[buf][a_k + 3][r] = ra[i].w;
-      *reinterpret_cast<float4*>(&Bs[buf][b_k + 8 * i][b_n]) = rb[i];
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(&Bs[buf][b_k + 8 * i][b_n]) = rb[i];
   };
 
-  float acc[8][8];
+  float acc[TR][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TR; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
@@ -103,14 +109,17 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
     if (kt + 1 < nk) load_tiles((kt + 1) * BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      float av[TR];
+#pragma unroll
+      for (int hh = 0; hh < RH; ++hh) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][64 * hh + ty * 4]);
+        av[4 * hh] = a0.x; av[4 * hh + 1] = a0.y; av[4 * hh + 2] = a0.z; av[4 * hh + 3] = a0.w;
+      }
       const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
       const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < TR; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs g) {
 
   // epilogue
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < TR; ++i) {
     const int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (row >= g.M) continue;
 #pragma unroll
@@ -188,6 +197,13 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t st) {
 }
 
 int launch_sgemm_train(const GemmArgs& g, cudaStream_t st) {
+  // fill the GPU: 64-row tiles when 128-row tiles would give fewer CTAs than two waves of SMs
+  if (ceil_div(g.M, BM) * (g.Nc / BN) < 296) {
+    dim3 grid(ceil_div(g.M, 64), g.Nc / BN);
+    sgemm_kernel<EPI_TRAIN, 64><<<grid, 256, 0, st>>>(g);
+    AGH_LAUNCH_CHECK();
+    return AGH_OK;
+  }
   dim3 grid(ceil_div(g.M, BM), g.Nc / BN);
   sgemm_kernel<EPI_TRAIN><<<grid, 256, 0, st>>>(g);
   AGH_LAUNCH_CHECK();

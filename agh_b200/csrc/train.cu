@@ -428,7 +428,7 @@ extern "C" int agh_gemm_f64(const double* A, int lda, int transA, const double* 
 extern "C" int agh_colsum(const float* X, long long ld, int M, int N, float* out, void* stream) {
   AGH_CHECK_ARG(X && out && M >= 0 && N > 0);
   if (M == 0) return AGH_OK;
-  const int rpb = 64;
+  const int rpb = 16;      // short serial loops, several hundred CTAs: the kernel is latency-bound, not bandwidth-bound
   colsum_kernel<<<ceil_div(M, rpb), 256, 0, (cudaStream_t)stream>>>(X, ld, M, N, rpb, out);
   AGH_LAUNCH_CHECK();
   return AGH_OK;

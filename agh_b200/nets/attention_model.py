@@ -108,10 +108,17 @@ class AttentionModel(nn.Module):
         self._sampling_seed, self._seed_calls = None, 0   # fixed Philox seed (else drawn from torch's generator per call)
         self.id_offset = 0               # global id of instance 0 of the batch (sharding-independent sampling)
         self._blob = None
-        self._blob_key = None
+        self._blob_key = (None, None)
         self._bn_dirty = False
+        self._plist = self._blist = self._pdict = self._bdict = None
         self._dist_dev = None
         self.last_steps = None           # [B] i32 steps per instance of the last rollout (device)
+
+    def _apply(self, fn, *args, **kw):
+        # .to() / .cuda() may replace the parameter tensors: drop the cached lists and the packed weights
+        self._plist = self._blist = self._pdict = self._bdict = None
+        self._blob = None
+        return super()._apply(fn, *args, **kw)
 
     # ------------------------------------------------------------------ plumbing
     def set_decode_type(self, decode_type, temp=None):
@@ -122,20 +129,44 @@ class AttentionModel(nn.Module):
     def _device(self):
         return self.project_out.weight.device
 
+    def _tensor_lists(self):
+        """(parameters, buffers) as lists, cached: the module structure is fixed after construction."""
+        if self._plist is None:
+            self._plist = [p for _, p in self.named_parameters()]
+            self._blist = [b for _, b in self.named_buffers()]
+        return self._plist, self._blist
+
     def weight_blob(self) -> torch.Tensor:
-        """Packed weights, re-packed whenever a parameter/buffer was modified in place or moved."""
-        tensors = list(self.parameters()) + list(self.buffers())
-        key = (self._device(), tuple(t._version for t in tensors), tuple(t.data_ptr() for t in tensors))
-        # the training kernels update the BatchNorm running statistics through raw pointers (no version bump): the
-        # eval-mode fold is re-packed at the first use outside training.  invalidate_blob() forces a re-pack after
-        # in-place edits through `.data`, which do not bump versions either.
-        stale_bn = self._bn_dirty and not self.training
-        if self._blob is None or key != self._blob_key or stale_bn:
+        """Packed weights, re-packed whenever a parameter was modified in place or moved -- and, outside training, whenever
+        a BatchNorm buffer changed: the packed BatchNorm fold (scale / shift from the running statistics) is only read by the
+        eval-mode encoder, so the ten train-mode forwards of a batch, each of which updates the statistics, share ONE pack."""
+        params, bufs = self._tensor_lists()
+        pkey = (self._device(), tuple(t._version for t in params), tuple(t.data_ptr() for t in params))
+        bkey = None if self.training else (tuple(t._version for t in bufs), tuple(t.data_ptr() for t in bufs))
+        # the training kernels update the running statistics through raw pointers (no version bump): _bn_dirty marks the
+        # fold stale until the first use outside training.  invalidate_blob() forces a re-pack after in-place edits through
+        # `.data`, which do not bump versions either.
+        stale = self._blob is None or pkey != self._blob_key[0]
+        if not self.training:
+            stale = stale or self._bn_dirty or bkey != self._blob_key[1]
+        if stale:
             if not self.training:
                 self._bn_dirty = False
+            else:
+                self._bn_dirty = True          # packed in training: the fold was built from whatever the buffers held
             self._blob = pack_weights(self.state_dict(), device=self._device())
-            self._blob_key = key
+            self._blob_key = (pkey, bkey)
         return self._blob
+
+    def _param_dict(self):
+        if self._pdict is None:
+            self._pdict = dict(self.named_parameters())
+            self._bdict = dict(self.named_buffers())
+        return self._pdict
+
+    def _buffer_dict(self):
+        self._param_dict()
+        return self._bdict
 
     def invalidate_blob(self):
         self._blob = None
@@ -202,8 +233,7 @@ class AttentionModel(nn.Module):
         with torch.no_grad():
             if self.training:
                 from .train_fn import encoder_train_forward
-                h, _ = encoder_train_forward(self, self.weight_blob(), task, dict(self.named_parameters()),
-                                             dict(self.named_buffers()), save=False)
+                h, _ = encoder_train_forward(self, self.weight_blob(), task, self._param_dict(), self._buffer_dict(), save=False)
                 return h.view(task.B, task.N + 1, -1)
             return ops.encode(self.weight_blob(), task)
 
@@ -215,8 +245,8 @@ class AttentionModel(nn.Module):
         need_grad = torch.is_grad_enabled() and self.training
         if need_grad:
             from .train_fn import FleetTrainFn
-            named = list(self.named_parameters())
-            ll, cost, serve, pi16, steps, status = FleetTrainFn.apply(self, task, [k for k, _ in named], *[p for _, p in named])
+            named = self._param_dict()
+            ll, cost, serve, pi16, steps, status = FleetTrainFn.apply(self, task, list(named.keys()), *named.values())
             out = {'pi': pi16, 'steps': steps}
         else:
             with torch.no_grad():

@@ -88,7 +88,7 @@ class FleetTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, task: FleetTask, names: List[str], *params):
         P: Dict[str, torch.Tensor] = dict(zip(names, params))
-        bufs = dict(model.named_buffers())
+        bufs = model._buffer_dict()
         B, n = task.B, task.N + 1
         blob = model.weight_blob()
         x, saved = encoder_train_forward(model, blob, task, P, bufs, save=True)
@@ -106,7 +106,7 @@ class FleetTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gll, *_unused):
         model, task, names = ctx.model, ctx.task, ctx.names
-        P = dict(model.named_parameters())
+        P = model._param_dict()
         out, keys, h, blob = ctx.out, ctx.keys, ctx.h, ctx.blob
         dev = h.device
         B, n, _ = h.shape

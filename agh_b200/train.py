@@ -188,7 +188,13 @@ def train_batch_agh(model, optimizer, baseline, epoch, batch_id, step, batch, tb
     assert bl_val is not None
     bl_val = move_to(bl_val, opts.device)
     set_decode_type(model, 'sampling')
-    costs, lls = fleet_rollout(model, x, opts.device)                    # costs [B,10], lls: 10 x [B] with grad
+    inner = get_inner_model(model)
+    defer, inner.defer_checks = inner.defer_checks, True                 # tour validity: one host sync per batch, not per fleet
+    try:
+        costs, lls = fleet_rollout(model, x, opts.device)                # costs [B,10], lls: 10 x [B] with grad
+        inner.raise_pending()
+    finally:
+        inner.defer_checks = defer
     loss = sum(((costs[:, i] - bl_val[:, i]) * lls[i]).mean() for i in range(len(lls))) / len(lls)
 
     optimizer.zero_grad()

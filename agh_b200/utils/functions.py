@@ -1,5 +1,7 @@
-"""Utilities on the AGH path: reference utils/functions.py (load_problem :13, move_to :32,
-load_model :80-130, do_batch_rep :171-179, sample_many :182-223, parse_softmax_temperature :133)."""
+"""Utilities on the AGH path: reference utils/functions.py (load_problem :13, move_to :32, load_model :80-130,
+parse_softmax_temperature :133).  The reference's do_batch_rep / sample_many (:171-223) have no counterpart here:
+AttentionModel.sample_many runs the replicas on ONE staged key set per instance (csrc/decode_shared.cu) and reduces them with
+agh_best_of instead of materialising batch_rep copies of every input."""
 from __future__ import annotations
 
 import json
@@ -7,7 +9,6 @@ import os
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 
 def load_problem(name):
@@ -87,31 +88,3 @@ def parse_softmax_temperature(raw_temp):
     if os.path.isfile(raw_temp):
         return np.loadtxt(raw_temp)[-1, 0]
     return float(raw_temp)
-
-
-def do_batch_rep(v, n):
-    if isinstance(v, dict):
-        return {k: do_batch_rep(v_, n) for k, v_ in v.items()}
-    if isinstance(v, (list, tuple)):
-        return type(v)(do_batch_rep(v_, n) for v_ in v)
-    return v[None, ...].expand(n, *v.size()).contiguous().view(-1, *v.size()[1:])
-
-
-def sample_many(inner_func, get_cost_func, input, batch_rep=1, iter_rep=1):
-    """Generic best-of-k driver with the reference's signature.  AttentionModel.sample_many does not
-    go through it (it shares the staged keys across replicas on the device); kept for callers that pass
-    their own inner/cost functions."""
-    input = do_batch_rep(input, batch_rep)
-    costs, pis, serves = [], [], []
-    for _ in range(iter_rep):
-        _log_p, pi, serve_time = inner_func(input)
-        cost, _ = get_cost_func(input, pi)
-        costs.append(cost.view(batch_rep, -1).t())
-        pis.append(pi.view(batch_rep, -1, pi.size(-1)).transpose(0, 1))
-        serves.append(serve_time.view(batch_rep, -1, serve_time.size(-1)).transpose(0, 1))
-    width = max(p.size(-1) for p in pis)
-    pis = torch.cat([F.pad(p, (0, width - p.size(-1))) for p in pis], 1)
-    costs, serves = torch.cat(costs, 1), torch.cat(serves, 1)
-    mincosts, arg = costs.min(-1)
-    rows = torch.arange(pis.size(0), device=arg.device)
-    return pis[rows, arg], mincosts, serves[rows, arg]

@@ -368,6 +368,38 @@ def test_results_do_not_depend_on_timing(cuda_model, n):
     assert torch.equal(first[:48], light)
 
 
+@pytest.mark.parametrize('n', [50, 100, 200])
+def test_sampling_and_replay_do_not_depend_on_timing(cuda_model, tables, n):
+    """The same race detector for the other decode modes: Philox sampling (per-instance CTAs and the shared-key kernel)
+    and action replay with the per-step dumps give bit-identical outputs on a saturated and on a lightly loaded GPU."""
+    from agh_b200 import _lib
+    base = {k: v[:500] for k, v in make_instances(n).items()}
+    task_cpu = {k: v for k, v in O.fleet_task(tables, base, 2, O.new_tw_left_levels(base)).items() if k != 'distance'}
+    big = to_task({k: v.repeat(6, *([1] * (v.dim() - 1))) for k, v in task_cpu.items()})       # 3000 CTAs: every SM loaded
+    small = to_task({k: v[:24] for k, v in task_cpu.items()})                                   # 24 CTAs
+    keys = ('pi', 'steps', 'll', 'cost', 'serve')
+    # sampling: global Philox ids make row r of the big batch (= instance r % 500) draw the noise of id r
+    heavy = cuda_forward(cuda_model, big, mode=_lib.AGH_SAMPLING, seed=5)
+    again = cuda_forward(cuda_model, big, mode=_lib.AGH_SAMPLING, seed=5)
+    light = cuda_forward(cuda_model, small, mode=_lib.AGH_SAMPLING, seed=5)
+    for k in keys:
+        assert torch.equal(heavy[k], again[k]), k
+        assert torch.equal(heavy[k][:24], light[k]), k
+    if n <= 100:      # shared-key kernel: 40 replicas of 75 / of 3 instances, same global ids
+        sh_heavy = cuda_forward(cuda_model, to_task({k: v[:75] for k, v in task_cpu.items()}), mode=_lib.AGH_SAMPLING, seed=9, reps=40)
+        sh_again = cuda_forward(cuda_model, to_task({k: v[:75] for k, v in task_cpu.items()}), mode=_lib.AGH_SAMPLING, seed=9, reps=40)
+        for k in keys:
+            assert torch.equal(sh_heavy[k], sh_again[k]), k
+    # replay of the sampled tours with every dump enabled
+    T = int(heavy['steps'].max())
+    rp_heavy = cuda_forward(cuda_model, big, mode=_lib.AGH_REPLAY, actions=heavy['pi'], replay_steps=T, want_dumps=True, want_logp_sel=True)
+    rp_light = cuda_forward(cuda_model, small, mode=_lib.AGH_REPLAY, actions=heavy['pi'][:24].contiguous(), replay_steps=T,
+                            want_dumps=True, want_logp_sel=True)
+    for k in ('ll', 'cost', 'serve', 'mask_dump', 'used_dump', 'cft_dump', 'logp_sel'):
+        assert torch.equal(rp_heavy[k][:24], rp_light[k]), k
+    assert torch.allclose(rp_heavy['ll'], heavy['ll'], rtol=1e-5, atol=1e-4)
+
+
 def test_get_costs_kernel(cuda_model, tables):
     from agh_b200 import AGH
     inst = {k: v[:64] for k, v in make_instances(20).items()}

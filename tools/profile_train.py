@@ -18,6 +18,7 @@ def main():
     ap.add_argument('--flights', type=int, default=100)
     ap.add_argument('--batch-size', type=int, default=64)
     ap.add_argument('--profile', action='store_true')
+    ap.add_argument('--cprofile', action='store_true', help='host-side profile of one step (cProfile, cumulative time)')
     args = ap.parse_args()
     from agh_b200 import AttentionModel, AGH, _lib, ops
     from agh_b200.train import fleet_rollout
@@ -25,6 +26,7 @@ def main():
     torch.manual_seed(1234); np.random.seed(1234)
     model = AttentionModel(128, 128, AGH).to(dev)
     model.train(); model.set_decode_type('sampling')
+    model.defer_checks = True          # one validity sync per batch (train_batch_agh does the same)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     ds = AGH.make_dataset(size=args.flights, num_samples=args.batch_size)
     bat = ds.arrays
@@ -37,6 +39,7 @@ def main():
         model.weight_blob()
         torch.cuda.synchronize(); t['pack_blob'] = time.perf_counter() - t0; t1 = time.perf_counter()
         costs, lls = fleet_rollout(model, bat, dev)
+        model.raise_pending()
         torch.cuda.synchronize(); t['forward_10_fleets'] = time.perf_counter() - t1; t2 = time.perf_counter()
         loss = sum(((costs[:, i] - bl[:, i]) * lls[i]).mean() for i in range(10)) / 10
         opt.zero_grad()
@@ -61,6 +64,16 @@ def main():
         opt.zero_grad(); loss.backward(); opt.step()
     e1.record(); torch.cuda.synchronize()
     print('5 steps: wall %.1f ms/step, device span %.1f ms/step' % (1e3 * (time.perf_counter() - w0) / 5, e0.elapsed_time(e1) / 5))
+    if args.cprofile:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(3):
+            step()
+        pr.disable()
+        st = pstats.Stats(pr)
+        st.sort_stats('tottime').print_stats(35)
     if args.profile:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
