@@ -4,7 +4,7 @@
 // (decode.cu) spends one CTA, 155 KB of staging and three block barriers per step on every replica; here ONE CTA stages the
 // instance's matrices once and each of its WARPS owns one replica for all T steps:
 //   * no block barrier in the step loop -- a replica's step is a chain of warp-synchronous phases (__syncwarp only), and
-//     8..16 independent replicas per SM hide each other's latencies;
+//     4..16 independent replicas per SM hide each other's latencies;
 //   * no redundant work -- the state update is done once per replica (every warp of the per-instance kernel repeats it);
 //   * every phase walks the compact list of the step's FEASIBLE nodes only;
 //   * phase mappings chosen so that no cross-lane reduction of the 128-wide glimpse is needed:
@@ -442,28 +442,40 @@ static int launch(const agh_decode_args& a, int reps, cudaStream_t st, bool* tak
   int dev = 0, max_smem = 0;
   AGH_CUDA(cudaGetDevice(&dev));
   AGH_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  // the widest CTA (most replicas per staged key set) that fits, with the step-context table resident when possible
-  const int wcand[3] = {16, 8, 4};
+  // Replicas per CTA (= warps, 4..16): the FEWEST that still put all replicas on the GPU in one wave (fewer warps per SM
+  // = a shorter step for each; e.g. 1 instance x 1280 replicas -> 143 CTAs of 9 warps instead of 80 of 16), else 16.
+  // The step-context table is resident when it fits.
+  int sms = 148;
+  AGH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int sm_smem = 0;
+  AGH_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
   for (int resp = 1; resp >= 0; --resp) {
-    for (int wi = 0; wi < 3; ++wi) {
-      const int warps = wcand[wi];
-      if (warps > reps && wi < 2 && wcand[wi + 1] >= reps) continue;       // do not launch mostly idle CTAs
+    int pick = 0;
+    for (int warps = 4; warps <= 16; ++warps) {
       const size_t bytes = layout(n, NPL, resp != 0, warps).total;
-      if ((int)bytes > max_smem) continue;
-      const int groups = (reps + warps - 1) / warps;
-      const long long grid = (long long)a.key_mod * groups;
-      if (grid > 2147483647LL) continue;
-      if (resp) {
-        AGH_CUDA(cudaFuncSetAttribute(decode_shared_kernel<NPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        decode_shared_kernel<NPL, true><<<(unsigned)grid, warps * 32, bytes, st>>>(a, reps);
-      } else {
-        AGH_CUDA(cudaFuncSetAttribute(decode_shared_kernel<NPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        decode_shared_kernel<NPL, false><<<(unsigned)grid, warps * 32, bytes, st>>>(a, reps);
-      }
-      AGH_LAUNCH_CHECK();
-      *taken = true;
-      return AGH_OK;
+      if ((int)bytes > max_smem) break;
+      pick = warps;                                                          // the largest that fits, unless one wave is reached
+      int per_sm = sm_smem / ((int)bytes + 1024);
+      per_sm = per_sm < 1 ? 1 : per_sm;
+      if (per_sm * warps > 16) per_sm = 16 / warps;                          // 512 threads x 128 registers fill the register file
+      const long long grid = (long long)a.key_mod * ((reps + warps - 1) / warps);
+      if (grid <= (long long)sms * per_sm) break;
     }
+    if (pick == 0) continue;
+    const int warps = pick;
+    const size_t bytes = layout(n, NPL, resp != 0, warps).total;
+    const long long grid = (long long)a.key_mod * ((reps + warps - 1) / warps);
+    if (grid > 2147483647LL) continue;
+    if (resp) {
+      AGH_CUDA(cudaFuncSetAttribute(decode_shared_kernel<NPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      decode_shared_kernel<NPL, true><<<(unsigned)grid, warps * 32, bytes, st>>>(a, reps);
+    } else {
+      AGH_CUDA(cudaFuncSetAttribute(decode_shared_kernel<NPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      decode_shared_kernel<NPL, false><<<(unsigned)grid, warps * 32, bytes, st>>>(a, reps);
+    }
+    AGH_LAUNCH_CHECK();
+    *taken = true;
+    return AGH_OK;
   }
   *taken = false;
   return AGH_OK;

@@ -141,20 +141,16 @@ def precompute(wblob, h, task: FleetTask):
     return keys, psc, qbase
 
 
-_travel_cache: Dict[tuple, torch.Tensor] = {}
-
-
 def travel_table(distance: torch.Tensor) -> torch.Tensor:
     """distance / 110 as the reference computes it (state_agh.py:118,167: an f32 IEEE division), once per table: the
     decode kernel's mask path loads the quotient instead of dividing every step.  Computed on the CPU (correctly
-    rounded f32 division) and cached per distance tensor."""
-    key = (distance.data_ptr(), distance._version, str(distance.device))
-    t = _travel_cache.get(key)
-    if t is None:
-        if len(_travel_cache) > 16:
-            _travel_cache.clear()
-        t = (distance.detach().cpu().to(torch.float32) / 110.0).to(distance.device).contiguous()
-        _travel_cache[key] = t
+    rounded f32 division) and kept ON the distance tensor object (with the version it was computed from), so a cache can
+    never outlive or be confused with another table."""
+    cached = getattr(distance, '_agh_travel', None)
+    if cached is not None and cached[0] == distance._version and cached[1].device == distance.device:
+        return cached[1]
+    t = (distance.detach().cpu().to(torch.float32) / 110.0).to(distance.device).contiguous()
+    distance._agh_travel = (distance._version, t)
     return t
 
 

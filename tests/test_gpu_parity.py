@@ -577,17 +577,18 @@ def test_large_sizes_properties(cuda_model, tables, weights, n, B):
         assert np.abs(out['h'].cpu().numpy() - h.numpy()).max() < 1e-4
 
 
-def test_training_step_matches_oracle(tables, weights):
-    """a18: one REINFORCE batch in train mode (batch-stat BatchNorm): loss and gradients equal the CPU
-    oracle's for the same sampled actions."""
+@pytest.mark.parametrize('n,B', [(20, 16), (50, 5)])
+def test_training_step_matches_oracle(tables, weights, n, B):
+    """a18: one REINFORCE batch in train mode (batch-stat BatchNorm) through the hand-written CUDA forward / backward
+    (nets/train_fn.py, csrc/train.cu): loss and all 62 parameter gradients equal the CPU oracle's (torch autograd over the
+    reference's formulation) for the same sampled actions."""
     from agh_b200 import AttentionModel, AGH
     from agh_b200.train import fleet_rollout
     torch.manual_seed(1234)
     model = AttentionModel(128, 128, AGH).cuda()
     model.train()
     model.set_decode_type('sampling')
-    B = 16
-    inst = {k: v[:B] for k, v in make_instances(20).items()}
+    inst = {k: v[:B] for k, v in make_instances(n).items()}
     bl = torch.from_numpy(np.random.RandomState(5).uniform(20000, 30000, size=(B, 10)).astype(np.float32))
     pis = []
     orig = model.forward

@@ -228,6 +228,12 @@ def _dist_worker(rank, ws, port, q):
     p.grad = torch.full((5,), float(rank + 1)); p2.grad = torch.full((2, 3), float(10 * (rank + 1)))
     parallel.allreduce_grads_([p, p2])
     ok = ok and torch.allclose(p.grad, torch.full((5,), 1.5)) and torch.allclose(p2.grad, torch.full((2, 3), 15.0))
+    # BatchNorm running statistics ride in the same bucket (integer buffers such as num_batches_tracked are skipped)
+    p.grad = torch.full((5,), float(rank + 1))
+    run_mean, run_var, tracked = torch.full((4,), float(rank)), torch.full((4,), 2.0 + 2 * rank), torch.tensor(7)
+    parallel.allreduce_grads_([p, p2], buffers=[run_mean, run_var, tracked])
+    ok = ok and torch.allclose(run_mean, torch.full((4,), 0.5)) and torch.allclose(run_var, torch.full((4,), 3.0)) and int(tracked) == 7
+    ok = ok and torch.allclose(p.grad, torch.full((5,), 1.5)) and torch.allclose(p2.grad, torch.full((2, 3), 15.0))
     q.put((rank, bool(ok), (lo, hi)))
     dist.destroy_process_group()
 
