@@ -2,7 +2,7 @@
 """Headline benchmark: AGH-100 greedy rollout throughput (BASELINE.json metric, config C3).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU port (oracle)
+    python bench.py --impl reference --gpus N --steps K ...  # the unmodified reference on the host cores (baseline/_ref)
 
 One "step" = one greedy rollout (all 10 fleets: assemble -> encode -> precompute -> fused decode ->
 cost) of one batch of `--batch` (default 10,000) synthetic AGH-100 instances per GPU.  Weak scaling:
@@ -14,8 +14,16 @@ every rank owns its own batch; no data-path collective.  Prints ONE 
              HOST arrays: H2D of the batch and D2H of the [B,10] cost table inside the timed region;
   roofline : the fused decode kernel against the measured HBM copy bandwidth, with
              A_step(N) = 1573 (N+1) + 1600 algorithmic bytes per instance-step (SURVEY 8d);
-  cpu_baseline : the oracle port (same algorithm in PyTorch-CPU ops, all host threads) on a bounded
-             sample of the same workload, rank 0, N=1 only.
+  roofline_onchip : the honest bound of that kernel: shared-memory wavefronts and FMA issue per instance-step;
+  cpu_baseline : the unmodified reference (baseline/_ref; else the oracle port) on the host cores, on a bounded
+             sample of the same workload, rank 0, N=1 only;
+  exact_tour_match : fraction of the seed-4321 AGH-20/50/100 validation instances whose 10 greedy fleet costs all
+             equal the reference's golden costs;
+  strong_scaling / train : two sub-records measured in the same run, so that the collectives run under the driver's
+             clock at every N: ONE batch of --batch instances sharded over the ranks with the cost-table all-gather
+             inside the timed region, and REINFORCE steps on a sharded global batch of --train-batch instances with
+             the gradient all-reduce inside the timed region (--no-extras skips them; --scaling strong / --workload train
+             run them alone).
 """
 import argparse
 import json
@@ -353,6 +361,24 @@ def run_cuda(args):
                                     'sample': 'first %d instances of the same batch in calls of 256, all 10 fleets, %.1f s' % (Bc, dt),
                                     'avg_cost_same_instances': {'cpu': float(ref.sum(1).mean()), 'gpu': float(mine.sum(1).mean())},
                                     'exact_tour_match_rate_same_instances': same}
+    # Two more records ride in the same line so that every driver run (N = 1, 2, 4, 8) also exercises the collectives:
+    # 'strong_scaling' = ONE batch of --batch instances sharded over the ranks, the [B/G,10] all-gather inside the timed
+    # region (configs[2] read literally); 'train' = REINFORCE steps on a global batch of --train-batch instances sharded
+    # over the ranks, the gradient all-reduce inside the timed region (configs[3]).  The headline fields above are untouched.
+    if not args.no_extras:
+        ctx = (dist, rank, ws, local, dev, barrier)
+        sub = types.SimpleNamespace(**vars(args))
+        sub.steps, sub.warmup, sub.no_cpu_baseline = min(args.steps, 5), 3, True
+        del model, resident
+        torch.cuda.empty_cache()
+        strong = strong_record(ctx, sub)
+        train = train_record(ctx, sub)
+        if rank == 0:
+            keep = ('value', 'unit', 'ms_per_step', 'scaling', 'config', 'e2e', 'gpu_launches', 'avg_cost',
+                    'checksum_rank0_equals_gather', 'ranks_hold_identical_weights', 'projected_epoch_12800_s', 'metric')
+            line['strong_scaling'] = {k: strong[k] for k in keep if k in strong}
+            line['train'] = {k: train[k] for k in keep if k in train}
+    if rank == 0:
         print(json.dumps(line))
     if ws > 1:
         dist.destroy_process_group()
@@ -377,7 +403,7 @@ def _dist_setup():
     return dist, rank, ws, local, dev, barrier
 
 
-def run_strong(args):
+def strong_record(ctx, args):
     """--scaling strong (BASELINE.json configs[2] read literally: ONE batch of 10,000 AGH-100 instances sharded over the
     ranks).  A step = train.rollout(model, dataset, opts): every rank copies its contiguous shard to the device, solves the
     10 fleets (same-level fleets batched into one launch sequence while a shard is below 16 k instance-fleets, which
@@ -386,7 +412,7 @@ def run_strong(args):
     the pinned-host copy and the D2H of the gathered table."""
     from agh_b200 import AttentionModel, AGH, AGHDataset, _lib, parallel
     from agh_b200.train import rollout, fleet_rollout
-    dist, rank, ws, local, dev, barrier = _dist_setup()
+    dist, rank, ws, local, dev, barrier = ctx
     N, B = args.flights, args.batch
     torch.manual_seed(1234)
     model = AttentionModel(128, 128, AGH).to(dev)
@@ -429,9 +455,10 @@ def run_strong(args):
     if ws > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_res, ms_e2e = t.tolist()
+    model.defer_checks = False
     if rank == 0:
         h2d = sum(v[lo:hi].numel() * v.element_size() for v in host.values())
-        print(json.dumps({
+        return ({
             'metric': METRIC, 'value': B / (ms_res * 1e-3), 'unit': UNIT, 'n_gpus': ws, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'AGH-%d greedy rollout, ONE batch of %d instances sharded over %d rank(s), 10 fleets (configs[2])' % (N, B, ws),
@@ -442,19 +469,27 @@ def run_strong(args):
             'e2e': {'value': B / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': B * 10 * 4,
                     'ms_per_step': ms_e2e, 'api': 'agh_b200.train.rollout(model, dataset, opts) under torch.distributed'},
             'gpu_launches': int(launches), 'avg_cost': float(host_costs.sum(1).mean()),
-            'checksum_rank0_equals_gather': bool(torch.equal(table.cpu(), host_costs))}))
-    if ws > 1:
-        dist.destroy_process_group()
+            'checksum_rank0_equals_gather': bool(torch.equal(table.cpu(), host_costs))})
+    return None
 
 
-def run_train(args):
+def run_strong(args):
+    ctx = _dist_setup()
+    line = strong_record(ctx, args)
+    if ctx[1] == 0:
+        print(json.dumps(line))
+    if ctx[2] > 1:
+        ctx[0].destroy_process_group()
+
+
+def train_record(ctx, args):
     """--workload train (BASELINE.json configs[3]): REINFORCE steps on a GLOBAL batch sharded over the ranks; one flat
     all-reduce of the 705,408 gradients (+ BatchNorm buffers) per step over NCCL (C1) inside the timed region.  A step =
     train.train_batch_agh: 10 sampling rollouts with the recorded per-step tensors, hand-written backward, all-reduce,
     clip, Adam.  Reports ms per global batch, instances/s and the projected 12,800-instance epoch."""
     from agh_b200 import AttentionModel, AGH, AGHDataset, _lib, parallel
     from agh_b200.train import train_batch_agh, rollout
-    dist, rank, ws, local, dev, barrier = _dist_setup()
+    dist, rank, ws, local, dev, barrier = ctx
     N, G = args.flights, args.train_batch
     torch.manual_seed(1234)
     model = AttentionModel(128, 128, AGH).to(dev)
@@ -522,9 +557,17 @@ def run_train(args):
             dt = time.perf_counter() - t0
             line['cpu_baseline'] = {'value': Bc / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                                     'sample': '%d instances: sampling rollout + REINFORCE loss + backward of the oracle port, %.1f s' % (Bc, dt)}
+        return line
+    return None
+
+
+def run_train(args):
+    ctx = _dist_setup()
+    line = train_record(ctx, args)
+    if ctx[1] == 0:
         print(json.dumps(line))
-    if ws > 1:
-        dist.destroy_process_group()
+    if ctx[2] > 1:
+        ctx[0].destroy_process_group()
 
 
 def main():
@@ -542,6 +585,7 @@ def main():
                     help='weak (default, the headline): --batch instances per GPU; strong: ONE batch of --batch instances sharded over the ranks')
     ap.add_argument('--workload', default='rollout', choices=['rollout', 'train'])
     ap.add_argument('--train-batch', type=int, default=512, help='--workload train: global batch')
+    ap.add_argument('--no-extras', action='store_true', help='skip the strong-scaling and training sub-records of the default run')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == 'reference':
