@@ -620,6 +620,41 @@ def test_training_step_matches_oracle(tables, weights, n, B):
     assert int(model.state_dict()['embedder.layers.0.1.normalizer.num_batches_tracked']) == 10
 
 
+def test_training_gradients_large_graph(tables, weights):
+    """The training path on the N > 127 variant of the rollout kernel (compact value / logit phases, V through L2 or shared
+    memory) and the 150-row attention backward: log-likelihood and parameter gradients of two fleet sub-problems against
+    the oracle's autograd on the same sampled actions."""
+    from agh_b200 import AttentionModel, AGH
+    from agh_b200.problems.agh.problem_agh import generate_arrays
+    torch.manual_seed(1234)
+    model = AttentionModel(128, 128, AGH).cuda()
+    model.train()
+    model.set_decode_type('sampling')
+    n, B = 200, 3
+    np.random.seed(17)
+    inst = generate_arrays(B, n)
+    lv = O.new_tw_left_levels(inst)
+    W = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in weights.items()}
+    coef = torch.tensor([1.0, -0.5, 2.0])
+    loss, ref_loss = 0.0, 0.0
+    for f in (1, 2):
+        task_cpu = O.fleet_task(tables, inst, f, lv)
+        cost, ll, serve, pi = model(to_task(task_cpu), return_pi=True)
+        out = O.forward(W, task_cpu, mode='replay', training=True, actions=pi.cpu())
+        assert np.allclose(ll.detach().cpu().numpy(), out['ll'].detach().numpy(), rtol=LOGP_RTOL, atol=2e-3)
+        assert np.array_equal(serve.cpu().numpy(), out['serve'].detach().numpy())
+        loss = loss + (coef.cuda() * ll).sum()
+        ref_loss = ref_loss + (coef * out['ll']).sum()
+        O.chain_tw_left(tables, lv, f, out['serve'].detach())
+    loss.backward()
+    ref_loss.backward()
+    gnorm = np.sqrt(sum(float((W[k].grad ** 2).sum()) for k, _ in model.named_parameters() if W[k].grad is not None))
+    for k, p in model.named_parameters():
+        gm, gr = p.grad.cpu().numpy(), W[k].grad.numpy()
+        denom = max(np.linalg.norm(gr), 1e-5 * gnorm)
+        assert np.linalg.norm(gm - gr) / denom < 5e-3, 'gradient of %s differs: %.3e' % (k, np.linalg.norm(gm - gr) / denom)
+
+
 @pytest.mark.parametrize('n,B', [(20, 7), (100, 300), (50, 1000), (200, 40), (300, 12)])
 def test_tensor_core_gemm_matches_cuda_core(cuda_model, tables, n, B):
     """tcgen05 split-FP16 GEMMs and mma.sync split-FP16 attention (encoder + precompute) against the fp32 CUDA-core path
