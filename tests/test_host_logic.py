@@ -313,3 +313,39 @@ def test_fp16_two_term_split_keeps_22_bits():
     ref = a.astype(np.float64) @ w.astype(np.float64).T
     scale = np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64).T
     assert (np.abs(got - ref) <= 2.0 ** -21 * scale).all()
+
+
+def test_greedy_near_tie_rule_equals_the_reference_selection():
+    """The selection contract of the decode kernels, restated in numpy and checked against the reference's own arithmetic
+    (torch: argmax_j exp(log_softmax(z))_j, first index on ties; attention_model.py:333,377,446-447): select the largest
+    logit unless a second one lies within NEAR_TIE = 2e-6 of it; then evaluate p_j = exp((z_j - max) - log(sum exp(z - max)))
+    for the candidates in that window and take the first index of the maximum.  Logits: equal values, 1-3 ulp apart far
+    below the rounding grid of log_p (the reference's exp(log_p) collapses them into a tie), and decisive gaps."""
+    rng = np.random.RandomState(3)
+    near_tie = np.float32(2e-6)
+
+    def kernel_rule(z):
+        zmax = z.max()
+        cand = np.nonzero(z >= zmax - near_tie)[0]
+        if len(cand) == 1:
+            return int(cand[0])
+        lse = np.log(np.exp((z - zmax).astype(np.float32)).sum(dtype=np.float32)).astype(np.float32)
+        p = np.exp(((z[cand] - zmax).astype(np.float32) - lse).astype(np.float32)).astype(np.float32)
+        return int(cand[np.argmax(p)])
+
+    not_largest = 0
+    for trial in range(3000):
+        n = int(rng.randint(2, 102))
+        base = np.float32(rng.uniform(2.0 ** -6, 2.0 ** -5 * 0.99))
+        kind = trial % 3
+        near = (np.full(n, base, np.float32).view(np.int32) + rng.randint(0, 4, n).astype(np.int32)).view(np.float32)
+        far = (base + rng.uniform(-5, 5, n)).astype(np.float32)
+        z = near if kind == 0 else far if kind == 1 else np.where(rng.rand(n) < 0.3, near + np.float32(6.0), far).astype(np.float32)
+        mask = rng.rand(n) < 0.4
+        mask[rng.randint(n)] = False
+        zt = torch.from_numpy(np.where(mask, -np.inf, z).astype(np.float32))
+        ref = int(torch.log_softmax(zt, -1).exp().max(0)[1])
+        mine = kernel_rule(zt.numpy())
+        assert mine == ref, (trial, kind, mine, ref)
+        not_largest += int(zt[ref] < zt.max())
+    assert not_largest > 100          # the reference often does NOT pick the largest logit: the rule matters
