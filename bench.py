@@ -293,9 +293,9 @@ def run_cuda(args):
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         # physical DRAM bytes per decode launch from the committed `ncu --set full` capture of this very workload
         # (ncu cannot run inside a timed benchmark: the figure is the committed capture of this round's kernel, refreshed
-        # whenever the kernel changes; profiles/r2c_decode_ncu_summary.md)
+        # whenever the kernel changes; profiles/r2x_decode_ncu_summary.md)
         traffic, onchip = None, None
-        tp = os.path.join(ROOT, 'profiles', 'r2c_decode_traffic.json')
+        tp = os.path.join(ROOT, 'profiles', 'r2x_decode_traffic.json')
         if os.path.exists(tp) and (N, B) == (100, 10000):
             prof = json.load(open(tp))
             traffic = prof['traffic_bytes_per_launch']
@@ -309,7 +309,7 @@ def run_cuda(args):
                       'frac_of_smem_floor': smem_floor / per_step_clk, 'frac_of_fma_floor': fma_floor / per_step_clk,
                       'ncu_this_round': {k: prof[k] for k in ('issue_active_pct', 'smem_pipe_pct_of_peak', 'fma_pipe_pct', 'alu_pipe_pct')},
                       'note': 'latency-bound: three block barriers and the serial select/update per step; '
-                              'profiles/r2c_decode_ncu_summary.md'}
+                              'profiles/r2x_decode_ncu_summary.md'}
         line = {
             'metric': METRIC, 'value': B * ws / (ms_res * 1e-3), 'unit': UNIT, 'n_gpus': ws, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -333,7 +333,7 @@ def run_cuda(args):
                          'instance_steps_per_launch': inst_steps_per_launch, 'launch_ms': dec_launch_ms,
                          'share_of_step': t_dec / ms_res,
                          'note': 'keys stay on chip (registers + shared memory) for all T steps, so the fraction exceeds 1: '
-                                 'physical DRAM traffic is the one-time staging only (profiles/r2c_decode_traffic.json); see roofline_onchip'},
+                                 'physical DRAM traffic is the one-time staging only (profiles/r2x_decode_traffic.json); see roofline_onchip'},
             'roofline_onchip': onchip,
             'roofline_encoder': {'kernels': 'gemm_tc_kernel + mha_mma_kernel + init_embed (agh_encode, agh_precompute)',
                                  'bound': 'tensor', 'achieved': enc_tflops, 'peak': tflops, 'unit': 'TFLOP/s',
