@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libagh_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['decode.cu', 'decode_shared.cu', 'encoder.cu', 'gemm_tc.cu', 'mha_mma.cu', 'env.cu', 'train.cu']
+SOURCES = ['decode.cu', 'decode_shared.cu', 'encoder.cu', 'gemm_tc.cu', 'ffn_tc.cu', 'mha_mma.cu', 'env.cu', 'train.cu']
 NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17']
 
@@ -33,7 +33,7 @@ class AghError(RuntimeError):
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile agh_b200/csrc/*.cu into agh_b200/libagh_b200.so (sm_100a, -lineinfo)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'gemm.cuh'), os.path.join(_HERE, '..', 'include', 'agh_b200.h')]
+    deps = srcs + [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'gemm.cuh'), os.path.join(CSRC, 'tc.cuh'), os.path.join(_HERE, '..', 'include', 'agh_b200.h')]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
@@ -111,6 +111,7 @@ SYMBOLS = {
     'agh_chain_tw_left': (_I, [_P, _I, _P, _I, _I, _P]),
     'agh_encoder_workspace_bytes': (C.c_size_t, [_I, _I]),
     'agh_set_gemm_backend': (_I, [_I]),
+    'agh_set_ffn_fused': (_I, [_I]),
     'agh_encode': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'agh_init_embed': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     'agh_encode_layers': (_I, [_P, _P, _I, _I, _P, _P, _P]),

@@ -344,7 +344,23 @@ extern "C" int agh_set_gemm_backend(int backend) {
 extern "C" size_t agh_encoder_workspace_bytes(int B, int N) {
   // qkv [M][384] + heads [M][128] + x1 [M][128] + hidden [M][512] + xa [M][128]
   const size_t M = (size_t)B * (N + 1);
-  return M * (3 * D + D + D + FF + D) * sizeof(float) + 256;
+  return M * (3 * D + D + D + FF + D) * sizeof(float) + 256 + ffn_tc_scratch_bytes() + 1024;
+}
+
+// AGH_FFN=unfused keeps the FF sublayer as two GEMMs with the hidden activations in HBM (A/B comparisons and tests)
+static int g_ffn_fused = -1;
+static bool use_fused_ffn() {
+  if (g_ffn_fused < 0) {
+    const char* e = getenv("AGH_FFN");
+    g_ffn_fused = (e != nullptr && strcmp(e, "unfused") == 0) ? 0 : 1;
+  }
+  return g_ffn_fused == 1 && use_tensor_cores() && ffn_tc_available();
+}
+
+extern "C" int agh_set_ffn_fused(int fused) {
+  if (fused != 0 && fused != 1) return AGH_E_ARG;
+  g_ffn_fused = fused;
+  return AGH_OK;
 }
 
 extern "C" int agh_init_embed(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
@@ -381,6 +397,13 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
   float* x1 = heads + (size_t)M * D;
   float* hid = x1 + (size_t)M * D;
   float* xa = hid + (size_t)M * FF;
+  // FP16-split FF weights of the fused feed-forward kernel: behind the activations, 1024-byte aligned
+  void* ffn_scratch = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(xa + (size_t)M * D) + 256 + 1023) & ~(uintptr_t)1023);
+  const bool ffn_fused = use_fused_ffn();
+  if (ffn_fused) {
+    const int rc = ffn_tc_split_weights(wblob, ffn_scratch, st);
+    if (rc) return rc;
+  }
   const float* x = h0;
   const int mha_threads = 128;                                     // 2 heads x 64 threads, 2 query rows per thread
   const size_t mha_smem = (size_t)n * 4 * HD * sizeof(float);
@@ -412,6 +435,12 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
     g.res = x; g.ldr = D; g.bn_s = lw + L_BN1S; g.bn_t = lw + L_BN1T;
     rc = launch_gemm<EPI_RES_BN>(g, st);
     if (rc) return rc;
+    if (ffn_fused) {
+      rc = launch_ffn_tc(x1, ffn_scratch, l, lw + L_B1, lw + L_B2, lw + L_BN2S, lw + L_BN2T, xout, M, st);
+      if (rc) return rc;
+      x = xout;
+      continue;
+    }
     g = GemmArgs{};
     g.A = x1; g.lda = D; g.W = lw + L_W1T; g.Wt = tw + T_W1; g.C = hid; g.ldc = FF; g.M = M; g.K = D; g.Nc = FF; g.bias = lw + L_B1;
     g.c_slab = tcg;

@@ -30,6 +30,14 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 // agh_gemm's fast path: plain row-major A [M][K] (lda) times W [K][N] (ld = N) through the tiled CUDA-core SGEMM
 int launch_sgemm_train(const GemmArgs& g, cudaStream_t st);
 
+// Fused FF sublayer on tcgen05 (ffn_tc.cu): y = BN(x + W2 relu(W1 x + b1) + b2) with the hidden activations kept on chip.
+// `scratch` (ffn_tc_scratch_bytes()) receives the FP16-split FF weights of all layers (ffn_tc_split_weights, once per call).
+bool ffn_tc_available();
+size_t ffn_tc_scratch_bytes();
+int ffn_tc_split_weights(const float* wblob, void* scratch, cudaStream_t st);
+int launch_ffn_tc(const float* x, const void* scratch, int layer, const float* b1, const float* b2, const float* bn_s,
+                  const float* bn_t, float* y, int M, cudaStream_t st);
+
 // Self-attention of all heads on mma.sync tensor cores (mha_mma.cu): qkv [B*n][384] (or slab-major [3][B*n][128]) -> heads [B*n][128].
 int launch_mha_mma(const float* qkv, bool slab_major, int B, int n, float* heads, cudaStream_t st);
 

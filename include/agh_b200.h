@@ -87,6 +87,9 @@ size_t agh_encoder_workspace_bytes(int B, int N);
 /* GEMM back end of agh_encode / agh_precompute: 1 = tcgen05 tensor cores with the two-term FP16 split (default; fp32-level accuracy),
  * 0 = fp32 CUDA-core SGEMM (kept for A/B measurements; env AGH_GEMM=simt selects it at load time) */
 int agh_set_gemm_backend(int backend);
+/* Feed-forward sublayer of the encoder: 1 = one fused tcgen05 kernel per layer, hidden activations kept on chip (default),
+ * 0 = two GEMMs with the [M][512] hidden activations in HBM (A/B measurements; env AGH_FFN=unfused selects it at load time) */
+int agh_set_ffn_fused(int fused);
 /* twr_f32: tw_right held f32 values in the caller (fleet 10) -> tw_right/1440 is an f32 division */
 int agh_encode(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
                const double* tw_right, int twr_f32, int B, int N, float* h_out, void* workspace, void* stream);
