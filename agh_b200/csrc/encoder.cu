@@ -457,6 +457,38 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
   return AGH_OK;
 }
 
+// Feed-forward sublayer of one encoder layer alone (graph_encoder.py:159-172 with eval-mode BatchNorm): y = BN2(x + FF(x)).
+// workspace: M * 512 floats (hidden activations of the two-GEMM form) + 256 + ffn scratch + 1024 bytes.
+extern "C" size_t agh_encoder_ffn_workspace_bytes(int M) {
+  return (size_t)M * FF * sizeof(float) + 256 + ffn_tc_scratch_bytes() + 1024;
+}
+
+extern "C" int agh_encoder_ffn(const float* wblob, int layer, const float* x, int M, float* y, void* workspace, void* stream) {
+  AGH_CHECK_ARG(wblob && x && y && workspace && M >= 0 && layer >= 0 && layer < LAYERS && x != y);
+  if (M == 0) return AGH_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* lw = wblob + W_LAYER0 + (size_t)layer * L_SIZE;
+  const float* tw = wblob + W_TC0 + (size_t)layer * T_SIZE;
+  float* hid = reinterpret_cast<float*>(workspace);
+  if (use_fused_ffn()) {
+    void* scratch = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(hid + (size_t)M * FF) + 256 + 1023) & ~(uintptr_t)1023);
+    int rc = ffn_tc_split_weights(wblob, scratch, st);
+    if (rc) return rc;
+    return launch_ffn_tc(x, scratch, layer, lw + L_B1, lw + L_B2, lw + L_BN2S, lw + L_BN2T, y, M, st);
+  }
+  const bool tcg = use_tensor_cores();
+  GemmArgs g{};
+  g.A = x; g.lda = D; g.W = lw + L_W1T; g.Wt = tw + T_W1; g.C = hid; g.ldc = FF; g.M = M; g.K = D; g.Nc = FF; g.bias = lw + L_B1;
+  g.c_slab = tcg;
+  int rc = launch_gemm<EPI_BIAS_RELU>(g, st);
+  if (rc) return rc;
+  g = GemmArgs{};
+  g.A = hid; g.lda = FF; g.W = lw + L_W2T; g.Wt = tw + T_W2; g.C = y; g.ldc = D; g.M = M; g.K = FF; g.Nc = D; g.bias = lw + L_B2;
+  g.res = x; g.ldr = D; g.bn_s = lw + L_BN2S; g.bn_t = lw + L_BN2T;
+  g.a_slab = tcg;
+  return launch_gemm<EPI_RES_BN>(g, st);
+}
+
 extern "C" int agh_encode(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
                           const double* tw_right, int twr_f32, int B, int N, float* h_out, void* workspace, void* stream) {
   AGH_CHECK_ARG(h_out != nullptr);

@@ -128,6 +128,16 @@ def encode_layers(wblob, h0) -> torch.Tensor:
     return h
 
 
+def encoder_ffn(wblob, layer: int, x) -> torch.Tensor:
+    """Feed-forward sublayer of encoder layer `layer` alone: BN2(x + W2 relu(W1 x + b1) + b2), x [M,128] (graph_encoder.py:159-172)."""
+    x = x.contiguous()
+    M = x.shape[0]
+    y = torch.empty_like(x)
+    ws = torch.empty(int(lib().agh_encoder_ffn_workspace_bytes(M)) // 4 + 1, dtype=torch.float32, device=x.device)
+    check(lib().agh_encoder_ffn(ptr(wblob, torch.float32), int(layer), ptr(x, torch.float32), M, ptr(y), ptr(ws), stream_ptr(x.device)))
+    return y
+
+
 def precompute(wblob, h, task: FleetTask):
     """a4: keys [3,B,n,128] (K', V, LK' as plain row-major matrices), psc [B,n,128], qbase [B,128]."""
     B, n, _ = h.shape

@@ -90,6 +90,10 @@ int agh_set_gemm_backend(int backend);
 /* Feed-forward sublayer of the encoder: 1 = one fused tcgen05 kernel per layer, hidden activations kept on chip (default),
  * 0 = two GEMMs with the [M][512] hidden activations in HBM (A/B measurements; env AGH_FFN=unfused selects it at load time) */
 int agh_set_ffn_fused(int fused);
+/* The feed-forward sublayer of encoder layer `layer` alone (graph_encoder.py:159-172, eval-mode BatchNorm):
+ *   y[M][128] = BN2(x + W2 relu(W1 x + b1) + b2);  x != y.  workspace: agh_encoder_ffn_workspace_bytes(M) bytes. */
+size_t agh_encoder_ffn_workspace_bytes(int M);
+int agh_encoder_ffn(const float* wblob, int layer, const float* x, int M, float* y, void* workspace, void* stream);
 /* twr_f32: tw_right held f32 values in the caller (fleet 10) -> tw_right/1440 is an f32 division */
 int agh_encode(const float* wblob, const uint8_t* coord, const float* demand, const float* tw_left,
                const double* tw_right, int twr_f32, int B, int N, float* h_out, void* workspace, void* stream);

@@ -687,3 +687,58 @@ def test_tensor_core_gemm_matches_cuda_core(cuda_model, tables, n, B):
     assert (h_t - h_s).abs().max().item() < 2e-4
     assert (keys_t - keys_s).abs().max().item() < 3e-5
     assert (psc_t - psc_s).abs().max().item() < 3e-5
+    # the fused feed-forward kernel (default above) against the two-GEMM form with the hidden activations in HBM
+    try:
+        lib.agh_set_ffn_fused(0)
+        h_u = ops.encode(blob, task)
+        torch.cuda.synchronize()
+    finally:
+        lib.agh_set_ffn_fused(1)
+    e = (h_u.double() - ref).abs()
+    assert e.max().item() < 2e-4 and e.mean().item() < 1e-5
+    assert (h_t - h_u).abs().max().item() < 5e-5
+
+
+@pytest.mark.parametrize('M', [1, 127, 128, 129, 4200, 148 * 128 + 5, 300007])
+def test_fused_feed_forward_kernel(cuda_model, M):
+    """ffn_tc.cu alone through agh_encoder_ffn: y = BN2(x + W2 relu(W1 x + b1) + b2) (graph_encoder.py:159-172, eval-mode
+    BatchNorm with non-trivial running statistics) against a float64 evaluation, for every layer, on row counts around
+    the 128-row tile, around one tile per SM and many tiles per SM; the two-GEMM form on the same input as a second witness.
+    Measured (relative to max(1, |y|)): fused max 3.2e-6 / mean 1.9e-7, two GEMMs max 1.7e-6 / mean 1.0e-7 -- the fused kernel
+    keeps ONE hi.hi accumulator for the K = 512 contraction (TMEM is full), the two-GEMM form spreads it over three."""
+    from agh_b200 import ops, _lib
+    import torch.nn.functional as F
+    lib = _lib.lib()
+    sd = {k: v.clone() for k, v in cuda_model.state_dict().items()}
+    g = torch.Generator(device='cuda').manual_seed(M)
+    try:
+        with torch.no_grad():
+            for k, v in cuda_model.state_dict().items():
+                if 'running_mean' in k: v.copy_(torch.randn(v.shape, generator=g, device='cuda') * 0.3)
+                if 'running_var' in k: v.copy_(torch.rand(v.shape, generator=g, device='cuda') * 1.5 + 0.5)
+                if k.endswith('normalizer.bias'): v.copy_(torch.randn(v.shape, generator=g, device='cuda') * 0.1)
+        cuda_model.invalidate_blob()
+        blob = cuda_model.weight_blob()
+        W = {k: v.double() for k, v in cuda_model.state_dict().items()}
+        x = torch.randn(M, 128, generator=g, device='cuda') * 2.0
+        for layer in range(3):
+            pre = 'embedder.layers.%d.' % layer
+            ff = F.linear(F.relu(F.linear(x.double(), W[pre + '2.module.0.weight'], W[pre + '2.module.0.bias'])),
+                          W[pre + '2.module.2.weight'], W[pre + '2.module.2.bias'])
+            nrm = pre + '3.normalizer.'
+            ref = (x.double() + ff - W[nrm + 'running_mean']) / torch.sqrt(W[nrm + 'running_var'] + 1e-5) * W[nrm + 'weight'] + W[nrm + 'bias']
+            y_f = ops.encoder_ffn(blob, layer, x)
+            lib.agh_set_ffn_fused(0)
+            y_u = ops.encoder_ffn(blob, layer, x)
+            lib.agh_set_ffn_fused(1)
+            torch.cuda.synchronize()
+            scale = ref.abs().clamp_min(1.0)
+            for name, y in (('fused', y_f), ('two GEMMs', y_u)):
+                e = (y.double() - ref).abs() / scale
+                print('feed-forward %s layer %d M=%d: max rel err %.3e mean %.3e' % (name, layer, M, e.max().item(), e.mean().item()))
+                assert e.max().item() < 6e-6, '%s feed-forward, layer %d, M=%d: max rel err %.3e' % (name, layer, M, e.max().item())
+                assert e.mean().item() < 4e-7, '%s feed-forward, layer %d, M=%d: mean rel err %.3e' % (name, layer, M, e.mean().item())
+    finally:
+        lib.agh_set_ffn_fused(1)
+        cuda_model.load_state_dict(sd)
+        cuda_model.invalidate_blob()

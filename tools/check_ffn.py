@@ -52,6 +52,16 @@ def main():
               % (n, B, ref.abs().max().item(), eu.max().item(), eu.mean().item(), ef.max().item(), ef.mean().item(),
                  (h_f - h_u).abs().max().item()), flush=True)
     if args.time:
+        x = torch.randn(1010000, 128, device='cuda')
+        for fused in (0, 1, 0, 1):
+            lib.agh_set_ffn_fused(fused)
+            for _ in range(3): ops.encoder_ffn(blob, 1, x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20): ops.encoder_ffn(blob, 1, x)
+            e1.record(); torch.cuda.synchronize()
+            print('FF sublayer alone, M = 1.01 M rows, fused=%d: %.1f us' % (fused, e0.elapsed_time(e1) * 50), flush=True)
         n, B = 100, 10000
         np.random.seed(3)
         inst = generate_arrays(B, n)
