@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libagh_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['decode.cu', 'decode_shared.cu', 'encoder.cu', 'gemm_tc.cu', 'ffn_tc.cu', 'mha_mma.cu', 'env.cu', 'train.cu']
+SOURCES = ['decode.cu', 'decode_shared.cu', 'encoder.cu', 'gemm_tc.cu', 'ffn_tc.cu', 'mha_mma.cu', 'mha_tc.cu', 'env.cu', 'train.cu']
 NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17']
 
@@ -112,6 +112,7 @@ SYMBOLS = {
     'agh_encoder_workspace_bytes': (C.c_size_t, [_I, _I]),
     'agh_set_gemm_backend': (_I, [_I]),
     'agh_set_ffn_fused': (_I, [_I]),
+    'agh_set_mha_tc': (_I, [_I]),
     'agh_encoder_ffn_workspace_bytes': (C.c_size_t, [_I]),
     'agh_encoder_ffn': (_I, [_P, _I, _P, _I, _P, _P, _P]),
     'agh_encode': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),

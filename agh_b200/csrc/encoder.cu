@@ -357,6 +357,22 @@ static bool use_fused_ffn() {
   return g_ffn_fused == 1 && use_tensor_cores() && ffn_tc_available();
 }
 
+// AGH_MHA=mma keeps the encoder attention on the mma.sync kernel for every graph size (A/B comparisons and tests)
+static int g_mha_tc = -1;
+static bool use_mha_tc() {
+  if (g_mha_tc < 0) {
+    const char* e = getenv("AGH_MHA");
+    g_mha_tc = (e != nullptr && strcmp(e, "mma") == 0) ? 0 : 1;
+  }
+  return g_mha_tc == 1;
+}
+
+extern "C" int agh_set_mha_tc(int on) {
+  if (on != 0 && on != 1) return AGH_E_ARG;
+  g_mha_tc = on;
+  return AGH_OK;
+}
+
 extern "C" int agh_set_ffn_fused(int fused) {
   if (fused != 0 && fused != 1) return AGH_E_ARG;
   g_ffn_fused = fused;
@@ -423,7 +439,10 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
     g.c_slab = qkv_slab;
     int rc = launch_gemm<EPI_PLAIN>(g, st);
     if (rc) return rc;
-    if (tcg && !mha_simt) {
+    if (tcg && !mha_simt && qkv_slab && use_mha_tc() && mha_tc_supported(n)) {
+      rc = launch_mha_tc(qkv, B, n, heads, st);
+      if (rc) return rc;
+    } else if (tcg && !mha_simt) {
       rc = launch_mha_mma(qkv, qkv_slab, B, n, heads, st);
       if (rc) return rc;
     } else {

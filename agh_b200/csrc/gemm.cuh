@@ -41,4 +41,8 @@ int launch_ffn_tc(const float* x, const void* scratch, int layer, const float* b
 // Self-attention of all heads on mma.sync tensor cores (mha_mma.cu): qkv [B*n][384] (or slab-major [3][B*n][128]) -> heads [B*n][128].
 int launch_mha_mma(const float* qkv, bool slab_major, int B, int n, float* heads, cudaStream_t st);
 
+// Self-attention on tcgen05 (mha_tc.cu) for graphs of up to 112 nodes; qkv slab-major [3][B*n][128].
+bool mha_tc_supported(int n);
+int launch_mha_tc(const float* qkv, int B, int n, float* heads, cudaStream_t st);
+
 }  // namespace agh

@@ -90,6 +90,9 @@ int agh_set_gemm_backend(int backend);
 /* Feed-forward sublayer of the encoder: 1 = one fused tcgen05 kernel per layer, hidden activations kept on chip (default),
  * 0 = two GEMMs with the [M][512] hidden activations in HBM (A/B measurements; env AGH_FFN=unfused selects it at load time) */
 int agh_set_ffn_fused(int fused);
+/* Encoder self-attention for graphs of up to 112 nodes: 1 = tcgen05 kernel with S / P / O in TMEM (default),
+ * 0 = the mma.sync kernel used for larger graphs (A/B measurements; env AGH_MHA=mma selects it at load time) */
+int agh_set_mha_tc(int on);
 /* The feed-forward sublayer of encoder layer `layer` alone (graph_encoder.py:159-172, eval-mode BatchNorm):
  *   y[M][128] = BN2(x + W2 relu(W1 x + b1) + b2);  x != y.  workspace: agh_encoder_ffn_workspace_bytes(M) bytes. */
 size_t agh_encoder_ffn_workspace_bytes(int M);

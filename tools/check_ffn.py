@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Fused feed-forward kernel (ffn_tc.cu) against the two-GEMM form and a float64 evaluation of the encoder, with timings.
-    python tools/check_ffn.py [--time]"""
+"""Fused feed-forward kernel (ffn_tc.cu) and tcgen05 attention (mha_tc.cu) against the two-GEMM / mma.sync forms and a float64
+evaluation of the encoder, with timings.
+    python tools/check_ffn.py [--time] [--mha]"""
 import argparse
 import os
 import sys
@@ -18,6 +19,7 @@ def to_task(task_cpu, dev='cuda'):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--time', action='store_true')
+    ap.add_argument('--mha', action='store_true', help='A/B the attention kernels instead of the feed-forward kernels')
     ap.add_argument('--shapes', default='20x7,100x300,50x1000,200x40,300x12')
     args = ap.parse_args()
     from agh_b200 import AttentionModel, AGH, ops, _lib
@@ -41,16 +43,33 @@ def main():
         inst = generate_arrays(B, n)
         task_cpu = O.fleet_task(tables, inst, 5, O.new_tw_left_levels(inst))
         task = to_task(task_cpu)
-        lib.agh_set_ffn_fused(0)
+        sw = lib.agh_set_mha_tc if args.mha else lib.agh_set_ffn_fused
+        sw(0)
         h_u = ops.encode(blob, task)
-        lib.agh_set_ffn_fused(1)
+        sw(1)
         h_f = ops.encode(blob, task)
         torch.cuda.synchronize()
         ref = O.encoder(W64, ops.init_embed(blob, task).double())
         eu = (h_u.double() - ref).abs(); ef = (h_f.double() - ref).abs()
-        print('AGH-%d B=%d: |h| max %.2f; vs float64: unfused max %.3e mean %.3e | fused max %.3e mean %.3e | fused vs unfused max %.3e'
+        print('AGH-%d B=%d: |h| max %.2f; vs float64: old max %.3e mean %.3e | new max %.3e mean %.3e | new vs old max %.3e'
               % (n, B, ref.abs().max().item(), eu.max().item(), eu.mean().item(), ef.max().item(), ef.mean().item(),
                  (h_f - h_u).abs().max().item()), flush=True)
+    if args.time and args.mha:
+        n, B = 100, 10000
+        np.random.seed(3)
+        inst = generate_arrays(B, n)
+        task = to_task(O.fleet_task(tables, inst, 5, O.new_tw_left_levels(inst)))
+        for on in (0, 1, 0, 1):
+            lib.agh_set_mha_tc(on)
+            for _ in range(3): ops.encode(blob, task)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10): ops.encode(blob, task)
+            e1.record(); torch.cuda.synchronize()
+            print('encode AGH-100 B=10000 tcgen05 attention=%d: %.3f ms' % (on, e0.elapsed_time(e1) / 10), flush=True)
+        lib.agh_set_mha_tc(1)
+        return
     if args.time:
         x = torch.randn(1010000, 128, device='cuda')
         for fused in (0, 1, 0, 1):
