@@ -113,6 +113,7 @@ SYMBOLS = {
     'agh_set_gemm_backend': (_I, [_I]),
     'agh_set_ffn_fused': (_I, [_I]),
     'agh_set_mha_tc': (_I, [_I]),
+    'agh_encoder_mha': (_I, [_P, _I, _I, _P, _P]),
     'agh_encoder_ffn_workspace_bytes': (C.c_size_t, [_I]),
     'agh_encoder_ffn': (_I, [_P, _I, _P, _I, _P, _P, _P]),
     'agh_encode': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),

@@ -476,6 +476,20 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
   return AGH_OK;
 }
 
+// Self-attention of all heads alone (graph_encoder.py:83-104): qkv slab-major [3][B*n][128] (Q, K, V stacked) -> heads [B*n][128],
+// through the kernel agh_encode_layers would pick for this graph size (tcgen05 up to 112 nodes unless switched off, else mma.sync).
+extern "C" int agh_encoder_mha(const float* qkv, int B, int N, float* heads, void* stream) {
+  AGH_CHECK_ARG(qkv && heads && B >= 0 && N >= 1 && N < AGH_MAX_N);
+  if (B == 0) return AGH_OK;
+  const int n = N + 1;
+  if (!use_tensor_cores()) {
+    set_error("agh_encoder_mha: the tensor-core back end is switched off (use agh_mha_fwd for the CUDA-core kernel)");
+    return AGH_E_UNSUPPORTED;
+  }
+  if (use_mha_tc() && mha_tc_supported(n)) return launch_mha_tc(qkv, B, n, heads, (cudaStream_t)stream);
+  return launch_mha_mma(qkv, true, B, n, heads, (cudaStream_t)stream);
+}
+
 // Feed-forward sublayer of one encoder layer alone (graph_encoder.py:159-172 with eval-mode BatchNorm): y = BN2(x + FF(x)).
 // workspace: M * 512 floats (hidden activations of the two-GEMM form) + 256 + ffn scratch + 1024 bytes.
 extern "C" size_t agh_encoder_ffn_workspace_bytes(int M) {

@@ -128,6 +128,14 @@ def encode_layers(wblob, h0) -> torch.Tensor:
     return h
 
 
+def encoder_mha(qkv, B: int, N: int) -> torch.Tensor:
+    """Self-attention of one encoder layer alone: qkv [3, B*(N+1), 128] (Q, K, V stacked) -> heads [B*(N+1), 128] (graph_encoder.py:83-104)."""
+    qkv = qkv.contiguous()
+    heads = torch.empty(B * (N + 1), D, dtype=torch.float32, device=qkv.device)
+    check(lib().agh_encoder_mha(ptr(qkv, torch.float32), int(B), int(N), ptr(heads), stream_ptr(qkv.device)))
+    return heads
+
+
 def encoder_ffn(wblob, layer: int, x) -> torch.Tensor:
     """Feed-forward sublayer of encoder layer `layer` alone: BN2(x + W2 relu(W1 x + b1) + b2), x [M,128] (graph_encoder.py:159-172)."""
     x = x.contiguous()

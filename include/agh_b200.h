@@ -93,6 +93,9 @@ int agh_set_ffn_fused(int fused);
 /* Encoder self-attention for graphs of up to 112 nodes: 1 = tcgen05 kernel with S / P / O in TMEM (default),
  * 0 = the mma.sync kernel used for larger graphs (A/B measurements; env AGH_MHA=mma selects it at load time) */
 int agh_set_mha_tc(int on);
+/* The self-attention of one encoder layer alone (graph_encoder.py:83-104, all 8 heads, no projection):
+ *   qkv [3][B*n][128] f32 (Q, K, V of all instances as three stacked row-major matrices) -> heads [B*n][128] f32 */
+int agh_encoder_mha(const float* qkv, int B, int N, float* heads, void* stream);
 /* The feed-forward sublayer of encoder layer `layer` alone (graph_encoder.py:159-172, eval-mode BatchNorm):
  *   y[M][128] = BN2(x + W2 relu(W1 x + b1) + b2);  x != y.  workspace: agh_encoder_ffn_workspace_bytes(M) bytes. */
 size_t agh_encoder_ffn_workspace_bytes(int M);

@@ -55,6 +55,16 @@ def main():
               % (n, B, ref.abs().max().item(), eu.max().item(), eu.mean().item(), ef.max().item(), ef.mean().item(),
                  (h_f - h_u).abs().max().item()), flush=True)
     if args.time and args.mha:
+        qkv = torch.randn(3, 10000 * 101, 128, device='cuda')
+        for on in (0, 1, 0, 1):
+            lib.agh_set_mha_tc(on)
+            for _ in range(3): ops.encoder_mha(qkv, 10000, 100)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20): ops.encoder_mha(qkv, 10000, 100)
+            e1.record(); torch.cuda.synchronize()
+            print('attention alone, AGH-100 B=10000, tcgen05=%d: %.1f us' % (on, e0.elapsed_time(e1) * 50), flush=True)
         n, B = 100, 10000
         np.random.seed(3)
         inst = generate_arrays(B, n)
