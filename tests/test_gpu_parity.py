@@ -742,3 +742,32 @@ def test_fused_feed_forward_kernel(cuda_model, M):
         lib.agh_set_ffn_fused(1)
         cuda_model.load_state_dict(sd)
         cuda_model.invalidate_blob()
+
+
+@pytest.mark.parametrize('N,B', [(1, 5), (20, 7), (50, 300), (100, 149), (100, 1000), (111, 33), (112, 9)])
+def test_tensor_core_attention_kernel(N, B):
+    """mha_tc.cu alone through agh_encoder_mha (graph_encoder.py:83-104: softmax(Q K^T / sqrt(16)) V per head, no projection)
+    against a float64 evaluation and against the mma.sync kernel on the same input: every node count class of the tcgen05
+    kernel (one key group, several, the full 112 keys with and without padding keys), instance counts below and above one per
+    SM, and N = 112 (n = 113 nodes), which is served by the mma.sync kernel."""
+    from agh_b200 import ops, _lib
+    lib = _lib.lib()
+    n = N + 1
+    g = torch.Generator(device='cuda').manual_seed(100 * N + B)
+    qkv = torch.randn(3, B * n, 128, generator=g, device='cuda')
+    qkv[0] *= 1.5                                           # scores up to ~ +-25 in base 2: sharp rows
+    q, k, v = (qkv[i].double().view(B, n, 8, 16).permute(0, 2, 1, 3) for i in range(3))
+    ref = torch.softmax(q @ k.transpose(2, 3) / 4.0, dim=-1) @ v              # [B, 8, n, 16]
+    ref = ref.permute(0, 2, 1, 3).reshape(B * n, 128)
+    try:
+        out_tc = ops.encoder_mha(qkv, B, N)
+        lib.agh_set_mha_tc(0)
+        out_mma = ops.encoder_mha(qkv, B, N)
+        torch.cuda.synchronize()
+    finally:
+        lib.agh_set_mha_tc(1)
+    for name, out in (('tcgen05', out_tc), ('mma.sync', out_mma)):
+        e = (out.double() - ref).abs()
+        print('attention %s N=%d B=%d: max err %.3e mean %.3e' % (name, N, B, e.max().item(), e.mean().item()))
+        assert e.max().item() < 5e-6, '%s attention N=%d B=%d: max abs err %.3e' % (name, N, B, e.max().item())
+        assert e.mean().item() < 3e-7, '%s attention N=%d B=%d: mean abs err %.3e' % (name, N, B, e.mean().item())

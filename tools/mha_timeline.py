@@ -27,6 +27,12 @@ def main():
             print('   G=%2d  S %7d +%5d +%4d | PV %7d +%5d +%4d | sm %7d  %7d  %7d (softmax %5d)' % (
                 G, r[3][G], r[4][G] - r[3][G], r[5][G] - r[4][G], r[6][G], r[7][G] - r[6][G], r[8][G] - r[7][G],
                 r[9 + 3 * gi][c], r[10 + 3 * gi][c], r[11 + 3 * gi][c], r[11 + 3 * gi][c] - r[10 + 3 * gi][c]))
+        if 16 in r:
+            print('  inside the softmax of group 0 (warp of lane quarter 0), ns after the scores were seen:')
+            print('   head: pass-1 loads landed | max done | chunk 0 / 1 / 2 loads landed | all chunks done | stores done | P published')
+            for c in range(8, 20):
+                t0 = r[10][c]
+                print('   %4d: ' % (2 * c) + ' '.join('%6d' % (r[k][c] - t0) for k in (16, 17, 18, 19, 20, 21, 22, 11)))
         print('  per instance: %.0f ns (heads 16..48)' % ((r[5][48] - r[5][16]) / 4.0))
 
 
