@@ -335,11 +335,12 @@ def run_cuda(args):
                          'note': 'keys stay on chip (registers + shared memory) for all T steps, so the fraction exceeds 1: '
                                  'physical DRAM traffic is the one-time staging only (profiles/r2x_decode_traffic.json); see roofline_onchip'},
             'roofline_onchip': onchip,
-            'roofline_encoder': {'kernels': 'gemm_tc_kernel + mha_mma_kernel + init_embed (agh_encode, agh_precompute)',
+            'roofline_encoder': {'kernels': 'gemm_tc_kernel (QKV, out-projection, decoder projection) + mha_tc_kernel + ffn_tc_kernel + init_embed (agh_encode, agh_precompute)',
                                  'bound': 'tensor', 'achieved': enc_tflops, 'peak': tflops, 'unit': 'TFLOP/s',
                                  'frac': enc_tflops / tflops, 'share_of_step': (t_enc + t_pre) / ms_res,
-                                 'note': 'tcgen05 kind::f16 with the two-term FP16 split (3 MMAs per product, fp32-level accuracy) + mma.sync m16n8k16 attention with the same split; '
-                                         'achieved counts algorithmic fp32 flops, peak is the measured bf16 cuBLAS figure'},
+                                 'note': 'all on tcgen05 kind::f16 with the two-term FP16 split (3 MMA-equivalents per product, fp32-level accuracy): GEMMs with fused epilogues, '
+                                         'attention with S / P / O in TMEM, the feed-forward sublayer as one kernel with the hidden activations on chip '
+                                         '(54 % of the dense FP16 tensor peak, profiles/r2_ffn_fused.md); achieved counts algorithmic fp32 flops, peak is the measured bf16 cuBLAS figure'},
             'phase_ms': {'encode': t_enc, 'precompute': t_pre, 'decode': t_dec},
             'decode_instance_steps_per_sec': total_inst_steps * ws / (ms_res * 1e-3),
             'avg_cost': float(host_costs.sum(1).mean()),
