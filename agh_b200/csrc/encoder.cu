@@ -348,33 +348,45 @@ extern "C" size_t agh_encoder_workspace_bytes(int B, int N) {
 }
 
 // AGH_FFN=unfused keeps the FF sublayer as two GEMMs with the hidden activations in HBM (A/B comparisons and tests)
+// The fused kernel is used for EVERY row count: results must not depend on how many instances share a launch (level-batched
+// fleets, shards of a multi-GPU batch and the tests rely on bit-identical per-instance results), and the two forms differ in the
+// last bits.  Measured per launch (tools/sweep_encoder_kernels.py, profiles/r2_encoder_kernel_sweep.md): it wins from about 20,000
+// rows (45 vs 48 us at M = 21,000; 788 vs 1,225 us at 1.01 M) and costs a few us below (33 vs 27 us at M = 1,344).
+// 1 = fused (default), 0 = two GEMMs, 2 = same as 1 (kept for symmetry with agh_set_mha_tc).
+constexpr int FFN_FUSED_MIN_ROWS = 0;
 static int g_ffn_fused = -1;
-static bool use_fused_ffn() {
+static bool use_fused_ffn(int M) {
   if (g_ffn_fused < 0) {
     const char* e = getenv("AGH_FFN");
-    g_ffn_fused = (e != nullptr && strcmp(e, "unfused") == 0) ? 0 : 1;
+    g_ffn_fused = (e != nullptr && strcmp(e, "unfused") == 0) ? 0 : (e != nullptr && strcmp(e, "fused") == 0) ? 2 : 1;
   }
-  return g_ffn_fused == 1 && use_tensor_cores() && ffn_tc_available();
+  if (!use_tensor_cores() || !ffn_tc_available()) return false;
+  return g_ffn_fused == 2 || (g_ffn_fused == 1 && M >= FFN_FUSED_MIN_ROWS);
 }
 
 // AGH_MHA=mma keeps the encoder attention on the mma.sync kernel for every graph size (A/B comparisons and tests)
+// The tcgen05 kernel always works on 112 key columns and 128 query rows; the mma.sync kernel's cost grows with n^2.  Measured
+// at B = 10,000: n = 101: 676 vs 1,057 us, n = 51: 835 vs 455 us, n = 21: 862 vs 188 us -> "auto" (1) takes the tcgen05 kernel
+// from 72 nodes; 2 forces it for every n <= 112 (unit tests).
+constexpr int MHA_TC_MIN_NODES = 72;
 static int g_mha_tc = -1;
-static bool use_mha_tc() {
+static bool use_mha_tc(int n) {
   if (g_mha_tc < 0) {
     const char* e = getenv("AGH_MHA");
-    g_mha_tc = (e != nullptr && strcmp(e, "mma") == 0) ? 0 : 1;
+    g_mha_tc = (e != nullptr && strcmp(e, "mma") == 0) ? 0 : (e != nullptr && strcmp(e, "tc") == 0) ? 2 : 1;
   }
-  return g_mha_tc == 1;
+  if (!mha_tc_supported(n)) return false;
+  return g_mha_tc == 2 || (g_mha_tc == 1 && n >= MHA_TC_MIN_NODES);
 }
 
 extern "C" int agh_set_mha_tc(int on) {
-  if (on != 0 && on != 1) return AGH_E_ARG;
+  if (on < 0 || on > 2) return AGH_E_ARG;
   g_mha_tc = on;
   return AGH_OK;
 }
 
 extern "C" int agh_set_ffn_fused(int fused) {
-  if (fused != 0 && fused != 1) return AGH_E_ARG;
+  if (fused < 0 || fused > 2) return AGH_E_ARG;
   g_ffn_fused = fused;
   return AGH_OK;
 }
@@ -415,7 +427,7 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
   float* xa = hid + (size_t)M * FF;
   // FP16-split FF weights of the fused feed-forward kernel: behind the activations, 1024-byte aligned
   void* ffn_scratch = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(xa + (size_t)M * D) + 256 + 1023) & ~(uintptr_t)1023);
-  const bool ffn_fused = use_fused_ffn();
+  const bool ffn_fused = use_fused_ffn(M);
   if (ffn_fused) {
     const int rc = ffn_tc_split_weights(wblob, ffn_scratch, st);
     if (rc) return rc;
@@ -439,7 +451,7 @@ extern "C" int agh_encode_layers(const float* wblob, const float* h0, int B, int
     g.c_slab = qkv_slab;
     int rc = launch_gemm<EPI_PLAIN>(g, st);
     if (rc) return rc;
-    if (tcg && !mha_simt && qkv_slab && use_mha_tc() && mha_tc_supported(n)) {
+    if (tcg && !mha_simt && qkv_slab && use_mha_tc(n)) {
       rc = launch_mha_tc(qkv, B, n, heads, st);
       if (rc) return rc;
     } else if (tcg && !mha_simt) {
@@ -486,7 +498,7 @@ extern "C" int agh_encoder_mha(const float* qkv, int B, int N, float* heads, voi
     set_error("agh_encoder_mha: the tensor-core back end is switched off (use agh_mha_fwd for the CUDA-core kernel)");
     return AGH_E_UNSUPPORTED;
   }
-  if (use_mha_tc() && mha_tc_supported(n)) return launch_mha_tc(qkv, B, n, heads, (cudaStream_t)stream);
+  if (use_mha_tc(n)) return launch_mha_tc(qkv, B, n, heads, (cudaStream_t)stream);
   return launch_mha_mma(qkv, true, B, n, heads, (cudaStream_t)stream);
 }
 
@@ -503,7 +515,7 @@ extern "C" int agh_encoder_ffn(const float* wblob, int layer, const float* x, in
   const float* lw = wblob + W_LAYER0 + (size_t)layer * L_SIZE;
   const float* tw = wblob + W_TC0 + (size_t)layer * T_SIZE;
   float* hid = reinterpret_cast<float*>(workspace);
-  if (use_fused_ffn()) {
+  if (use_fused_ffn(M)) {
     void* scratch = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(hid + (size_t)M * FF) + 256 + 1023) & ~(uintptr_t)1023);
     int rc = ffn_tc_split_weights(wblob, scratch, st);
     if (rc) return rc;

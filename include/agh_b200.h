@@ -87,11 +87,13 @@ size_t agh_encoder_workspace_bytes(int B, int N);
 /* GEMM back end of agh_encode / agh_precompute: 1 = tcgen05 tensor cores with the two-term FP16 split (default; fp32-level accuracy),
  * 0 = fp32 CUDA-core SGEMM (kept for A/B measurements; env AGH_GEMM=simt selects it at load time) */
 int agh_set_gemm_backend(int backend);
-/* Feed-forward sublayer of the encoder: 1 = one fused tcgen05 kernel per layer, hidden activations kept on chip (default),
- * 0 = two GEMMs with the [M][512] hidden activations in HBM (A/B measurements; env AGH_FFN=unfused selects it at load time) */
+/* Feed-forward sublayer of the encoder: 1 (default) or 2 = one fused tcgen05 kernel per layer with the hidden activations kept on
+ * chip, for every row count (the choice must not depend on the batch size: per-instance results are bit-identical across batch
+ * sizes); 0 = two GEMMs with the [M][512] hidden activations in HBM (A/B measurements and tests; env AGH_FFN=unfused selects it) */
 int agh_set_ffn_fused(int fused);
-/* Encoder self-attention for graphs of up to 112 nodes: 1 = tcgen05 kernel with S / P / O in TMEM (default),
- * 0 = the mma.sync kernel used for larger graphs (A/B measurements; env AGH_MHA=mma selects it at load time) */
+/* Encoder self-attention: 1 = auto (default): the tcgen05 kernel with S / P / O in TMEM for graphs of 72 .. 112 nodes, the mma.sync
+ * kernel otherwise (a function of the graph size only, never of the batch size); 0 = always mma.sync; 2 = tcgen05 for every graph of up to 112 nodes (A/B measurements and tests; env
+ * AGH_MHA=mma / tc selects 0 / 2 at load time) */
 int agh_set_mha_tc(int on);
 /* The self-attention of one encoder layer alone (graph_encoder.py:83-104, all 8 heads, no projection):
  *   qkv [3][B*n][128] f32 (Q, K, V of all instances as three stacked row-major matrices) -> heads [B*n][128] f32 */

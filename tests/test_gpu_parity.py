@@ -670,11 +670,15 @@ def test_tensor_core_gemm_matches_cuda_core(cuda_model, tables, n, B):
         h_s = ops.encode(blob, task)
         keys_s, psc_s, qb_s = ops.precompute(blob, h_s, task)
         lib.agh_set_gemm_backend(1)
+        lib.agh_set_ffn_fused(2)                 # the fused feed-forward and (up to 112 nodes) the tcgen05 attention kernel,
+        lib.agh_set_mha_tc(2)                    # whatever the size thresholds of the default configuration would pick
         h_t = ops.encode(blob, task)
         keys_t, psc_t, qb_t = ops.precompute(blob, h_s, task)
         torch.cuda.synchronize()
     finally:
         lib.agh_set_gemm_backend(1)
+        lib.agh_set_ffn_fused(1)
+        lib.agh_set_mha_tc(1)
     # 12 chained GEMMs + 3 attentions with split (hi + lo') operands; |h| reaches ~13.  Both back ends are judged against a float64
     # evaluation of the same layers: the split products carry ~2^-21 relative error each, a few times the fp32 FMA
     # chain's, which stays fp32-level after three layers.
@@ -687,16 +691,20 @@ def test_tensor_core_gemm_matches_cuda_core(cuda_model, tables, n, B):
     assert (h_t - h_s).abs().max().item() < 2e-4
     assert (keys_t - keys_s).abs().max().item() < 3e-5
     assert (psc_t - psc_s).abs().max().item() < 3e-5
-    # the fused feed-forward kernel (default above) against the two-GEMM form with the hidden activations in HBM
+    # the same against the two-GEMM feed-forward + mma.sync attention form, and against what the default configuration picks
     try:
         lib.agh_set_ffn_fused(0)
+        lib.agh_set_mha_tc(0)
         h_u = ops.encode(blob, task)
         torch.cuda.synchronize()
     finally:
         lib.agh_set_ffn_fused(1)
-    e = (h_u.double() - ref).abs()
-    assert e.max().item() < 2e-4 and e.mean().item() < 1e-5
-    assert (h_t - h_u).abs().max().item() < 5e-5
+        lib.agh_set_mha_tc(1)
+    h_d = ops.encode(blob, task)
+    for hh in (h_u, h_d):
+        e = (hh.double() - ref).abs()
+        assert e.max().item() < 2e-4 and e.mean().item() < 1e-5
+        assert (h_t - hh).abs().max().item() < 5e-5
 
 
 @pytest.mark.parametrize('M', [1, 127, 128, 129, 4200, 148 * 128 + 5, 300007])
@@ -727,6 +735,7 @@ def test_fused_feed_forward_kernel(cuda_model, M):
                           W[pre + '2.module.2.weight'], W[pre + '2.module.2.bias'])
             nrm = pre + '3.normalizer.'
             ref = (x.double() + ff - W[nrm + 'running_mean']) / torch.sqrt(W[nrm + 'running_var'] + 1e-5) * W[nrm + 'weight'] + W[nrm + 'bias']
+            lib.agh_set_ffn_fused(2)
             y_f = ops.encoder_ffn(blob, layer, x)
             lib.agh_set_ffn_fused(0)
             y_u = ops.encoder_ffn(blob, layer, x)
@@ -760,6 +769,7 @@ def test_tensor_core_attention_kernel(N, B):
     ref = torch.softmax(q @ k.transpose(2, 3) / 4.0, dim=-1) @ v              # [B, 8, n, 16]
     ref = ref.permute(0, 2, 1, 3).reshape(B * n, 128)
     try:
+        lib.agh_set_mha_tc(2)
         out_tc = ops.encoder_mha(qkv, B, N)
         lib.agh_set_mha_tc(0)
         out_mma = ops.encoder_mha(qkv, B, N)
