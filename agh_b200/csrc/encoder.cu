@@ -23,36 +23,51 @@ namespace agh {
 // ------------------------------------------------------------------------------------------
 // init embedding
 // ------------------------------------------------------------------------------------------
-__global__ void init_embed_kernel(const float* __restrict__ w, const uint8_t* __restrict__ coord,
+// One warp writes 32 consecutive rows: lane r first computes the three node features of row r (two of them divisions, one in
+// f64 -- once per row instead of once per output element), then the warp walks the rows with the features broadcast and every
+// lane producing 4 of the 128 columns; the lane's slices of the feature weights and bias stay in registers.
+__global__ void __launch_bounds__(256) init_embed_kernel(const float* __restrict__ w, const uint8_t* __restrict__ coord,
                                   const float* __restrict__ demand, const float* __restrict__ tw_left,
                                   const double* __restrict__ tw_right, int twr_f32, int B, int N, float* __restrict__ h0) {
   const int n = N + 1;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 4 columns)
-  const size_t total = (size_t)B * n * (D / 4);
-  if (idx >= total) return;
-  const int c4 = (int)(idx % (D / 4));
-  const size_t row = idx / (D / 4);
-  const int j = (int)(row % n);
-  const size_t b = row / n;
-  const int loc = coord[row];
-  float4 v = reinterpret_cast<const float4*>(w + W_LOC_EMB + (size_t)loc * D)[c4];
-  if (j >= 1) {
-    // features are concatenated in f64 when tw_right is f64 and then cast to f32
-    // (attention_model.py:290-292): demand and tw_left/1440 are f32 values, tw_right/1440 is an
-    // f64 division rounded to f32 (an f32 division when tw_right is f32: fleet 10).
-    const float f0 = demand[b * N + (j - 1)];
-    const float f1 = __fdiv_rn(tw_left[row], 1440.0f);
-    const float f2 = twr_f32 ? __fdiv_rn((float)tw_right[row], 1440.0f) : (float)(tw_right[row] / 1440.0);
-    const float4 w0 = reinterpret_cast<const float4*>(w + W_INIT_W)[c4];
-    const float4 w1 = reinterpret_cast<const float4*>(w + W_INIT_W + D)[c4];
-    const float4 w2 = reinterpret_cast<const float4*>(w + W_INIT_W + 2 * D)[c4];
-    const float4 bb = reinterpret_cast<const float4*>(w + W_INIT_B)[c4];
-    v.x += fmaf(w2.x, f2, fmaf(w1.x, f1, fmaf(w0.x, f0, bb.x)));
-    v.y += fmaf(w2.y, f2, fmaf(w1.y, f1, fmaf(w0.y, f0, bb.y)));
-    v.z += fmaf(w2.z, f2, fmaf(w1.z, f1, fmaf(w0.z, f0, bb.z)));
-    v.w += fmaf(w2.w, f2, fmaf(w1.w, f1, fmaf(w0.w, f0, bb.w)));
+  const int lane = threadIdx.x & 31;
+  const size_t rows = (size_t)B * n;
+  const size_t row0 = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  if (row0 >= rows) return;
+  const size_t row = row0 + lane;
+  int loc = 0, node = 0;
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  if (row < rows) {
+    const int j = (int)(row % n);
+    const size_t b = row / n;
+    loc = coord[row];
+    node = j >= 1;
+    if (node) {
+      // features are concatenated in f64 when tw_right is f64 and then cast to f32
+      // (attention_model.py:290-292): demand and tw_left/1440 are f32 values, tw_right/1440 is an
+      // f64 division rounded to f32 (an f32 division when tw_right is f32: fleet 10).
+      f0 = demand[b * N + (j - 1)];
+      f1 = __fdiv_rn(tw_left[row], 1440.0f);
+      f2 = twr_f32 ? __fdiv_rn((float)tw_right[row], 1440.0f) : (float)(tw_right[row] / 1440.0);
+    }
   }
-  reinterpret_cast<float4*>(h0 + row * D)[c4] = v;
+  const float4 w0 = reinterpret_cast<const float4*>(w + W_INIT_W)[lane];
+  const float4 w1 = reinterpret_cast<const float4*>(w + W_INIT_W + D)[lane];
+  const float4 w2 = reinterpret_cast<const float4*>(w + W_INIT_W + 2 * D)[lane];
+  const float4 bb = reinterpret_cast<const float4*>(w + W_INIT_B)[lane];
+  const int cnt = (int)(rows - row0 < 32 ? rows - row0 : 32);
+  for (int i = 0; i < cnt; ++i) {
+    const int loc_i = __shfl_sync(0xffffffffu, loc, i), node_i = __shfl_sync(0xffffffffu, node, i);
+    const float g0 = __shfl_sync(0xffffffffu, f0, i), g1 = __shfl_sync(0xffffffffu, f1, i), g2 = __shfl_sync(0xffffffffu, f2, i);
+    float4 v = reinterpret_cast<const float4*>(w + W_LOC_EMB + (size_t)loc_i * D)[lane];
+    if (node_i) {
+      v.x += fmaf(w2.x, g2, fmaf(w1.x, g1, fmaf(w0.x, g0, bb.x)));
+      v.y += fmaf(w2.y, g2, fmaf(w1.y, g1, fmaf(w0.y, g0, bb.y)));
+      v.z += fmaf(w2.z, g2, fmaf(w1.z, g1, fmaf(w0.z, g0, bb.z)));
+      v.w += fmaf(w2.w, g2, fmaf(w1.w, g1, fmaf(w0.w, g0, bb.w)));
+    }
+    reinterpret_cast<float4*>(h0 + (row0 + i) * D)[lane] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -395,8 +410,8 @@ extern "C" int agh_init_embed(const float* wblob, const uint8_t* coord, const fl
                               const double* tw_right, int twr_f32, int B, int N, float* h0, void* stream) {
   AGH_CHECK_ARG(wblob && coord && demand && tw_left && tw_right && h0 && B >= 0 && N >= 1);
   if (B == 0) return AGH_OK;
-  const size_t total = (size_t)B * (N + 1) * (D / 4);
-  init_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wblob, coord, demand, tw_left, tw_right,
+  const size_t warps = ((size_t)B * (N + 1) + 31) / 32;        // one warp per 32 rows, 8 warps per block
+  init_embed_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(wblob, coord, demand, tw_left, tw_right,
                                                                                      twr_f32, B, N, h0);
   AGH_LAUNCH_CHECK();
   return AGH_OK;

@@ -103,56 +103,81 @@ __global__ void generate_kernel(uint64_t seed, long long id_offset, int B, int N
 }
 
 // ---- a13: problem_agh.py:18-66, one warp per instance ----
+// Validity first (every flight exactly once: a per-warp visit counter in shared memory), then the replay of the tour: the
+// per-step operands (demand, node location, travel distance, window, duration) are fetched by the lanes in parallel, 32 steps
+// at a time, and the sequential recurrences (capacity, length, clock) are evaluated by every lane on shuffled copies -- the
+// same operations in the same order as the reference's loop, without a chain of dependent loads per step.
+constexpr int GC_WARPS = 4;
 template <typename PiT>
-__global__ void get_costs_kernel(const PiT* __restrict__ pi, int T, const uint8_t* __restrict__ coord,
+__global__ void __launch_bounds__(GC_WARPS * 32) get_costs_kernel(const PiT* __restrict__ pi, int T, const uint8_t* __restrict__ coord,
                                  const float* __restrict__ demand, const float* __restrict__ tw_left,
                                  const double* __restrict__ tw_right, const double* __restrict__ duration,
                                  const float* __restrict__ dist, int B, int N, float* __restrict__ cost,
                                  int32_t* __restrict__ status) {
+  __shared__ unsigned int s_cnt[GC_WARPS][AGH_MAX_N + 1];
   const int n = N + 1;
   const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (b >= B) return;
   const PiT* p = pi + (size_t)b * T;
+  unsigned int* cnt = s_cnt[wib];
   int st = 0;
   // (1) tour is zeros plus a permutation of 1..N (problem_agh.py:21-27): count visits per node
   int bad = 0;
-  for (int j = 1 + lane; j <= N; j += 32) {
-    int cnt = 0;
-    for (int t = 0; t < T; ++t) cnt += (p[t] == j);
-    bad |= (cnt != 1);
+  for (int j = lane; j <= N; j += 32) cnt[j] = 0u;
+  __syncwarp();
+  for (int t = lane; t < T; t += 32) {
+    const int a = (int)p[t];
+    if (a < 0 || a > N) bad = 1;
+    else if (a > 0) atomicAdd(&cnt[a], 1u);
   }
-  for (int t = lane; t < T; t += 32) bad |= (p[t] < 0 || p[t] > N);
+  __syncwarp();
+  for (int j = 1 + lane; j <= N; j += 32) bad |= (cnt[j] != 1u);
   if (__any_sync(0xffffffffu, bad)) st |= AGH_TOUR_INVALID;
   if (st) {                         // indices are not safe to replay
     if (lane == 0) { status[b] = st; cost[b] = 0.f; }
     return;
   }
-  // (2)+(3) sequential replay by lane 0
-  if (lane == 0) {
-    float used = 0.f, total = 0.f;
-    double cur = -60.0;
-    int prev_c = 0;
-    for (int t = 0; t < T; ++t) {
-      const int a = (int)p[t];
-      const float dem = a == 0 ? -1.0f : demand[(size_t)b * N + a - 1];
-      used = __fadd_rn(used, dem);
+  // (2)+(3) replay
+  float used = 0.f, total = 0.f;
+  double cur = -60.0;
+  int carry_c = 0;                  // location of the node before the chunk (the depot's location index is 0 at t = 0)
+  for (int base = 0; base < T; base += 32) {
+    const int t = base + lane;
+    const bool in = t < T;
+    const int a = in ? (int)p[t] : 0;
+    const size_t k = (size_t)b * n + a;
+    const float dem = a == 0 ? -1.0f : demand[(size_t)b * N + a - 1];
+    const int c = in ? (int)coord[k] : 0;
+    const float twl = tw_left[k];
+    const double dur = duration[k], twr = tw_right[k];
+    int pc = __shfl_up_sync(0xffffffffu, c, 1);
+    if (lane == 0) pc = carry_c;
+    const float d = dist[NODE_SIZE * pc + c];
+    const float tt = __fdiv_rn(d, 110.0f);
+    const int cnt_steps = min(32, T - base);
+    for (int i = 0; i < cnt_steps; ++i) {
+      const int ai = __shfl_sync(0xffffffffu, a, i);
+      const float demi = __shfl_sync(0xffffffffu, dem, i), di = __shfl_sync(0xffffffffu, d, i);
+      used = __fadd_rn(used, demi);
       if (used < 0.f) used = 0.f;
       if (!(used <= 1.0f + 1e-5f)) st |= AGH_CAPACITY_EXCEEDED;
-      const int c = coord[(size_t)b * n + a];
-      const float d = dist[NODE_SIZE * prev_c + c];
-      total = __fadd_rn(total, d);
-      if (a != 0) {
+      total = __fadd_rn(total, di);
+      const double twri = __shfl_sync(0xffffffffu, twr, i);
+      if (ai != 0) {
         // first step: cur_time is int64 -60 (problem_agh.py:58) so the sum is f32; identical result
-        const float tt = __fdiv_rn(d, 110.0f);
-        cur = __dadd_rn(fmax(__dadd_rn(cur, (double)tt), (double)tw_left[(size_t)b * n + a]), duration[(size_t)b * n + a]);
+        const float tti = __shfl_sync(0xffffffffu, tt, i), twli = __shfl_sync(0xffffffffu, twl, i);
+        const double duri = __shfl_sync(0xffffffffu, dur, i);
+        cur = __dadd_rn(fmax(__dadd_rn(cur, (double)tti), (double)twli), duri);
       } else {
         cur = -60.0;
       }
-      if (!(cur <= tw_right[(size_t)b * n + a] + 1e-5)) st |= AGH_TW_VIOLATED;
-      prev_c = c;
+      if (!(cur <= twri + 1e-5)) st |= AGH_TW_VIOLATED;
     }
-    total = __fadd_rn(total, dist[NODE_SIZE * prev_c]);
+    carry_c = __shfl_sync(0xffffffffu, c, cnt_steps - 1);
+  }
+  if (lane == 0) {
+    total = __fadd_rn(total, dist[NODE_SIZE * carry_c]);
     cost[b] = total;
     status[b] = st;
   }
@@ -285,7 +310,7 @@ extern "C" int agh_get_costs(const void* pi, int pi_elem_bytes, int T, const uin
   AGH_CHECK_ARG(B >= 0 && N >= 1 && T >= 1 && (pi_elem_bytes == 8 || pi_elem_bytes == 2));
   if (B == 0) return AGH_OK;
   const size_t threads = (size_t)B * 32;
-  const unsigned grid = (unsigned)((threads + 127) / 128);
+  const unsigned grid = (unsigned)((threads + 127) / 128);      // GC_WARPS warps per block
   if (pi_elem_bytes == 8)
     get_costs_kernel<int64_t><<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int64_t*>(pi), T, coord, demand, tw_left,
                                                                       tw_right, duration, distance, B, N, cost, status);
