@@ -385,6 +385,85 @@ __global__ void __launch_bounds__(128) tf_dquery_kernel(const float* __restrict_
   atomicAdd(dwtime + c, at);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Weight gradients: C[I][J] += sum_k A[k][i] B[k][j] with K = the number of rows of the batch (tens of thousands) and I, J <= 512.
+// Both operands are read along their rows (coalesced float4), 128 x 128 tile, 8 x 8 outputs per thread, double-buffered shared
+// memory, the K range split over enough CTAs for two per SM; partial tiles are added to C with vector atomics (C is zeroed by the
+// caller, as for the split-K form of the generic kernel).
+// ------------------------------------------------------------------------------------------
+constexpr int TN_T = 128, TN_K = 16;
+__global__ void __launch_bounds__(256, 2) sgemm_tn_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
+                                                          long long ldb, float* __restrict__ C, long long ldc, int I, int J, int K,
+                                                          int kchunk) {
+  __shared__ __align__(16) float As[2][TN_K][TN_T];
+  __shared__ __align__(16) float Bs[2][TN_K][TN_T];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.x * TN_T, j0 = blockIdx.y * TN_T;
+  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  if (kbeg >= kend) return;
+  const int lrow = tid >> 5, lcol = (tid & 31) * 4;            // this thread's float4 of a [16][128] tile: rows lrow, lrow + 8
+  float4 ra[2], rb[2];
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int k = k0 + lrow + 8 * r;
+      ra[r] = (k < kend && i0 + lcol < I) ? *reinterpret_cast<const float4*>(A + (size_t)k * lda + i0 + lcol) : z4;
+      rb[r] = (k < kend && j0 + lcol < J) ? *reinterpret_cast<const float4*>(B + (size_t)k * ldb + j0 + lcol) : z4;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      *reinterpret_cast<float4*>(&As[buf][lrow + 8 * r][lcol]) = ra[r];
+      *reinterpret_cast<float4*>(&Bs[buf][lrow + 8 * r][lcol]) = rb[r];
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  load_tiles(kbeg);
+  store_tiles(0);
+  __syncthreads();
+  const int nk = (kend - kbeg + TN_K - 1) / TN_K;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles(kbeg + (kt + 1) * TN_K);
+#pragma unroll
+    for (int kk = 0; kk < TN_K; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (row >= I) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int col = j0 + jh * 64 + tx * 4;
+      if (col >= J) continue;
+      atomicAdd(reinterpret_cast<float4*>(C + (size_t)row * ldc + col),
+                make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]));
+    }
+  }
+}
+
 }  // namespace agh
 
 using namespace agh;
@@ -407,6 +486,26 @@ extern "C" int agh_gemm(const agh_gemm_desc* desc, void* stream) {
     a.A = g.A; a.lda = (int)g.lda; a.W = g.B; a.C = g.C; a.ldc = (int)g.ldc; a.M = g.M; a.K = g.K; a.Nc = g.N;
     a.bias = g.bias; a.relu = g.relu; a.accumulate = g.accumulate; a.mask = g.mask; a.ldm = (int)g.ldm;
     return launch_sgemm_train(a, (cudaStream_t)stream);
+  }
+  // weight gradients (op(A) = A^T with a long reduction, C zeroed by the caller and filled by split-K atomics)
+  if (g.transA && !g.transB && g.batch1 * g.batch2 == 1 && g.splits > 1 && g.alpha == 1.0f && g.K >= 2048 && g.M >= 64 &&
+      g.M % 4 == 0 && g.N % 4 == 0 && g.lda % 4 == 0 && g.ldb % 4 == 0 && g.ldc % 4 == 0 &&
+      ((uintptr_t)g.A | (uintptr_t)g.B | (uintptr_t)g.C) % 16 == 0) {
+    const int tiles = ceil_div(g.M, TN_T) * ceil_div(g.N, TN_T);
+    int sm = 148;
+    {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int S = ceil_div(2 * sm, tiles);                          // two CTAs per SM
+    S = S < 1 ? 1 : (S > g.K / 128 ? g.K / 128 : S);
+    int kchunk = ceil_div(ceil_div(g.K, S), TN_K) * TN_K;
+    S = ceil_div(g.K, kchunk);
+    dim3 grid(ceil_div(g.M, TN_T), ceil_div(g.N, TN_T), (unsigned)S);
+    sgemm_tn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K, kchunk);
+    AGH_LAUNCH_CHECK();
+    return AGH_OK;
   }
   const long long z = (long long)g.batch1 * g.batch2 * g.splits;
   AGH_CHECK_ARG(z <= 65535);
