@@ -202,6 +202,8 @@ static bool use_tensor_cores() {
   return g_gemm_backend == 1;
 }
 
+bool gemm_tc_enabled() { return use_tensor_cores(); }
+
 template <int EPI>
 static int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   if (use_tensor_cores() && g.Wt != nullptr) return launch_gemm_tc<EPI>(g, st);

@@ -27,6 +27,9 @@ struct GemmArgs {
 template <int EPI>
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 
+// whether the tensor-core back end is selected (agh_set_gemm_backend / AGH_GEMM)
+bool gemm_tc_enabled();
+
 // agh_gemm's fast path: plain row-major A [M][K] (lda) times W [K][N] (ld = N) through the tiled CUDA-core SGEMM
 int launch_sgemm_train(const GemmArgs& g, cudaStream_t st);
 

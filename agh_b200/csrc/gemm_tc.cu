@@ -78,7 +78,7 @@ __host__ __device__ constexpr bool epi_transposed(int epi) { return (AGH_TC_TRAN
 // the other epilogues): decoder projection 736 vs 830 us, but QKV 646 vs 608, FF1 923 vs 812, out-proj 377 vs 292,
 // FF2 1024 vs 968 -- the shuffles were not what bounds those shapes -- so only the decoder projection uses it.
 #ifndef AGH_TC_SWAP_MASK
-#define AGH_TC_SWAP_MASK 0xb
+#define AGH_TC_SWAP_MASK 0x1b
 #endif
 __host__ __device__ constexpr bool epi_swap(int epi) { return (AGH_TC_SWAP_MASK >> epi) & 1; }
 #ifndef AGH_TC_FRAG_MASK
@@ -311,7 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int cl = q * 32 + lane, col = n0 + cl;
         const int r_first = chalf * CH_PER_WARP * 32, r_last = r_first + (CH_PER_WARP - 1) * 32;
         float bias = 0.f, sc = 1.f, sh = 0.f;
-        if (EPI == EPI_BIAS_RELU || (EPI == EPI_RES_BN && g.bias != nullptr)) bias = s_vec[cl];
+        if (EPI == EPI_BIAS_RELU || ((EPI == EPI_RES_BN || EPI == EPI_TRAIN) && g.bias != nullptr)) bias = s_vec[cl];
         if (EPI == EPI_RES_BN) { sc = s_vec[BN + cl]; sh = s_vec[2 * BN + cl]; }
         float rs[32];                                           // residual of rows mt*BM + rc + i, this thread's column
         auto load_res_sw = [&](int rc) {
@@ -358,7 +358,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           const int rbase = mt * BM + rc;
           float* dst = Cb + (size_t)rbase * ldc + col;
-          if (rbase + 32 <= g.M) {          // every row tile but the last: no per-row predicates
+          if (EPI == EPI_TRAIN) {           // training primitive on the tensor cores: v = acc [+ bias] [relu] (agh_gemm keeps the
+#pragma unroll                              // accumulate / mask forms on the CUDA-core kernels: their extra loads do not fit the
+            for (int i = 0; i < 32; ++i) {  // register budget of this epilogue)
+              float v = r[i] + bias;
+              if (g.relu) v = fmaxf(v, 0.f);
+              if (rbase + i < g.M) dst[(size_t)i * ldc] = v;
+            }
+          } else if (rbase + 32 <= g.M) {          // every row tile but the last: no per-row predicates
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               float v = r[i];
@@ -630,5 +637,6 @@ template int launch_gemm_tc<EPI_PLAIN>(const GemmArgs&, cudaStream_t);
 template int launch_gemm_tc<EPI_BIAS_RELU>(const GemmArgs&, cudaStream_t);
 template int launch_gemm_tc<EPI_RES_BN>(const GemmArgs&, cudaStream_t);
 template int launch_gemm_tc<EPI_DEC>(const GemmArgs&, cudaStream_t);
+template int launch_gemm_tc<EPI_TRAIN>(const GemmArgs&, cudaStream_t);
 
 }  // namespace agh

@@ -487,6 +487,18 @@ extern "C" int agh_gemm(const agh_gemm_desc* desc, void* stream) {
     a.bias = g.bias; a.relu = g.relu; a.accumulate = g.accumulate; a.mask = g.mask; a.ldm = (int)g.ldm;
     return launch_sgemm_train(a, (cudaStream_t)stream);
   }
+  // Activation-sized products against a K-major weight matrix (op(B) = B^T with B = [N][K], the layout the tcgen05 GEMM reads):
+  // on the tensor cores from 16,384 rows (the two-term FP16 split keeps fp32-level accuracy; below that the launch latency of
+  // the persistent kernel exceeds the CUDA-core SGEMM's whole run time)
+  if (!g.transA && g.transB && g.batch1 * g.batch2 == 1 && g.splits == 1 && g.alpha == 1.0f && g.M >= 16384 && gemm_tc_enabled() &&
+      !g.accumulate && g.mask == nullptr &&
+      (g.K == 128 || g.K % 64 == 0) && g.N % 128 == 0 && g.ldb == g.K && g.lda % 4 == 0 && g.ldc % 4 == 0 &&
+      ((uintptr_t)g.A | (uintptr_t)g.B) % 16 == 0) {
+    GemmArgs a{};
+    a.A = g.A; a.lda = (int)g.lda; a.Wt = g.B; a.C = g.C; a.ldc = (int)g.ldc; a.M = g.M; a.K = g.K; a.Nc = g.N;
+    a.bias = g.bias; a.relu = g.relu;
+    return launch_gemm_tc<EPI_TRAIN>(a, (cudaStream_t)stream);
+  }
   // weight gradients (op(A) = A^T with a long reduction, C zeroed by the caller and filled by split-K atomics)
   if (g.transA && !g.transB && g.batch1 * g.batch2 == 1 && g.splits > 1 && g.alpha == 1.0f && g.K >= 2048 && g.M >= 64 &&
       g.M % 4 == 0 && g.N % 4 == 0 && g.lda % 4 == 0 && g.ldb % 4 == 0 && g.ldc % 4 == 0 &&

@@ -41,10 +41,29 @@ def _layer_views(blob: torch.Tensor, l: int):
     v = lambda k, n: blob[base + o['l_' + k]: base + o['l_' + k] + n]
     tb = o['tc0'] + l * o['t_size']
     t = lambda k, n: blob[tb + o[k]: tb + o[k] + n]
-    # the transposed ([out][in]) copies turn every activation-gradient product dX = dY W^T into a plain row-major GEMM
+    # every weight in both layouts, [in][out] and [out][in]: an activation-sized product C = A W is either a plain row-major
+    # GEMM against the [K][N] copy (the register-tiled CUDA-core SGEMM) or, from TC_MIN_ROWS rows, a product against the K-major
+    # [N][K] copy with transB, which agh_gemm runs on the tcgen05 kernel (_act_gemm below)
     return {'wqkv': v('wqkv', D * 3 * D), 'wo': v('wo', D * D), 'w1t': v('w1t', D * FF), 'b1': v('b1', FF),
             'w2t': v('w2t', FF * D), 'b2': v('b2', D),
             'wqkv_T': t('t_wqkv', 3 * D * D), 'wo_T': t('t_wo', D * D), 'w1': t('t_w1', FF * D), 'w2': t('t_w2', D * FF)}
+
+
+TC_MIN_ROWS = 16384      # agh_gemm's threshold for the tensor-core path (csrc/train.cu)
+
+
+def _act_gemm(A, w_kn, w_nk, C, M, N, K, lda, ldc, accumulate=False, mask=None, ldm=0, **kw):
+    """C[M,N] = A[M,K] W (+ bias, ReLU, mask, accumulate): w_kn is W as [K][N], w_nk the same matrix as [N][K].  From TC_MIN_ROWS
+    rows the product runs on the tcgen05 kernel (bias / ReLU fused); masking and accumulation are then one element-wise pass."""
+    if M >= TC_MIN_ROWS and ldc == N:
+        out = torch.empty_like(C) if accumulate else C
+        ops.gemm(A, w_nk, out, M, N, K, lda, K, ldc, transB=True, **kw)
+        if mask is not None:
+            out.view(M, N).mul_(mask.view(M, N) > 0)
+        if accumulate:
+            C.add_(out)
+        return C
+    return ops.gemm(A, w_kn, C, M, N, K, lda, N, ldc, accumulate=accumulate, mask=mask, ldm=ldm, **kw)
 
 
 def encoder_train_forward(model, blob, task: FleetTask, P, bufs, save: bool):
@@ -60,16 +79,16 @@ def encoder_train_forward(model, blob, task: FleetTask, P, bufs, save: bool):
         w = _layer_views(blob, l)
         pre = 'embedder.layers.%d.' % l
         qkv = torch.empty(M, 3 * D, dtype=torch.float32, device=dev)
-        ops.gemm(x, w['wqkv'], qkv, M, 3 * D, D, D, 3 * D, 3 * D)
+        _act_gemm(x, w['wqkv'], w['wqkv_T'], qkv, M, 3 * D, D, D, 3 * D)
         heads = ops.mha_fwd(qkv, B, N)
         z1 = x.clone()
-        ops.gemm(heads, w['wo'], z1, M, D, D, D, D, D, accumulate=True)
+        _act_gemm(heads, w['wo'], w['wo_T'], z1, M, D, D, D, D, accumulate=True)
         y1, m1, r1 = ops.bn_train_fwd(z1, P[pre + '1.normalizer.weight'], P[pre + '1.normalizer.bias'],
                                       bufs[pre + '1.normalizer.running_mean'], bufs[pre + '1.normalizer.running_var'], scratch)
         hid = torch.empty(M, FF, dtype=torch.float32, device=dev)
-        ops.gemm(y1, w['w1t'], hid, M, FF, D, D, FF, FF, bias=w['b1'], relu=True)
+        _act_gemm(y1, w['w1t'], w['w1'], hid, M, FF, D, D, FF, bias=w['b1'], relu=True)
         z2 = y1.clone()
-        ops.gemm(hid, w['w2t'], z2, M, D, FF, FF, D, D, bias=w['b2'], accumulate=True)
+        _act_gemm(hid, w['w2t'], w['w2'], z2, M, D, FF, FF, D, bias=w['b2'], accumulate=True)
         y2, m2, r2 = ops.bn_train_fwd(z2, P[pre + '3.normalizer.weight'], P[pre + '3.normalizer.bias'],
                                       bufs[pre + '3.normalizer.running_mean'], bufs[pre + '3.normalizer.running_var'], scratch)
         bufs[pre + '1.normalizer.num_batches_tracked'].add_(1)
@@ -191,21 +210,21 @@ class FleetTrainFn(torch.autograd.Function):
             G[pre + '2.module.2.weight'] = ops.gemm(dz2, hid, torch.zeros(D, FF, **f32), D, FF, M, D, FF, FF, transA=True,
                                                     splits=_splits(M))
             dhid = torch.empty(M, FF, **f32)
-            ops.gemm(dz2, w['w2'], dhid, M, FF, D, D, FF, FF, mask=hid, ldm=FF)                  # (dz2 W2) o (hid > 0)
+            _act_gemm(dz2, w['w2'], w['w2t'], dhid, M, FF, D, D, FF, mask=hid, ldm=FF)          # (dz2 W2) o (hid > 0)
             G[pre + '2.module.0.bias'] = ops.colsum(dhid, M, FF)
             G[pre + '2.module.0.weight'] = ops.gemm(dhid, y1, torch.zeros(FF, D, **f32), FF, D, M, FF, D, D, transA=True,
                                                     splits=_splits(M))
-            ops.gemm(dhid, w['w1'], dz2, M, D, FF, FF, D, D, accumulate=True)                    # dy1 = dz2 + dhid W1
+            _act_gemm(dhid, w['w1'], w['w1t'], dz2, M, D, FF, FF, D, accumulate=True)            # dy1 = dz2 + dhid W1
             dz1, G[pre + '1.normalizer.weight'], G[pre + '1.normalizer.bias'] = ops.bn_train_bwd(
                 dz2, z1, m1, r1, P[pre + '1.normalizer.weight'], scratch)
             G[pre + '0.module.W_out'] = ops.gemm(heads, dz1, torch.zeros(D, D, **f32), D, D, M, D, D, D, transA=True,
                                                  splits=_splits(M)).view(H, HD, D)
-            dheads = ops.gemm(dz1, w['wo_T'], torch.empty(M, D, **f32), M, D, D, D, D, D)
+            dheads = _act_gemm(dz1, w['wo_T'], w['wo'], torch.empty(M, D, **f32), M, D, D, D, D)
             dqkv = ops.mha_bwd(qkv, heads, dheads, B, N)
             dwqkv = ops.gemm(x, dqkv, torch.zeros(D, 3 * D, **f32), D, 3 * D, M, D, 3 * D, 3 * D, transA=True, splits=_splits(M))
             for i, nm in enumerate(('W_query', 'W_key', 'W_val')):
                 G[pre + '0.module.' + nm] = dwqkv[:, i * D:(i + 1) * D].reshape(D, H, HD).permute(1, 0, 2).contiguous()
-            ops.gemm(dqkv, w['wqkv_T'], dz1, M, D, 3 * D, 3 * D, D, D, accumulate=True)          # dx = dz1 + dqkv Wqkv^T
+            _act_gemm(dqkv, w['wqkv_T'], w['wqkv'], dz1, M, D, 3 * D, 3 * D, D, accumulate=True)  # dx = dz1 + dqkv Wqkv^T
             dy = dz1
 
         # ---------------- init embedding (attention_model.py:272-294) ----------------

@@ -655,6 +655,73 @@ def test_training_gradients_large_graph(tables, weights):
         assert np.linalg.norm(gm - gr) / denom < 5e-3, 'gradient of %s differs: %.3e' % (k, np.linalg.norm(gm - gr) / denom)
 
 
+def test_training_gradients_tensor_core_rows(tables, weights):
+    """The training path with more than 16,384 rows per fleet (B = 170 at N = 100), where the activation-sized GEMMs of the
+    encoder's forward and backward run on the tcgen05 kernel (EPI_TRAIN epilogue: bias / ReLU / mask / accumulate) and the weight
+    gradients on the split-K TN kernel: log-likelihood and parameter gradients of two fleet sub-problems against the oracle's
+    autograd on the same sampled actions."""
+    from agh_b200 import AttentionModel, AGH
+    from agh_b200.problems.agh.problem_agh import generate_arrays
+    torch.manual_seed(1234)
+    model = AttentionModel(128, 128, AGH).cuda()
+    model.train()
+    model.set_decode_type('sampling')
+    n, B = 100, 170
+    np.random.seed(17)
+    inst = generate_arrays(B, n)
+    lv = O.new_tw_left_levels(inst)
+    W = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in weights.items()}
+    coef = torch.linspace(-1.0, 2.0, B)
+    loss, ref_loss = 0.0, 0.0
+    for f in (1, 2):
+        task_cpu = O.fleet_task(tables, inst, f, lv)
+        cost, ll, serve, pi = model(to_task(task_cpu), return_pi=True)
+        out = O.forward(W, task_cpu, mode='replay', training=True, actions=pi.cpu())
+        assert np.allclose(ll.detach().cpu().numpy(), out['ll'].detach().numpy(), rtol=LOGP_RTOL, atol=2e-3)
+        assert np.array_equal(serve.cpu().numpy(), out['serve'].detach().numpy())
+        loss = loss + (coef.cuda() * ll).sum()
+        ref_loss = ref_loss + (coef * out['ll']).sum()
+        O.chain_tw_left(tables, lv, f, out['serve'].detach())
+    loss.backward()
+    ref_loss.backward()
+    gnorm = np.sqrt(sum(float((W[k].grad ** 2).sum()) for k, _ in model.named_parameters() if W[k].grad is not None))
+    for k, p in model.named_parameters():
+        gm, gr = p.grad.cpu().numpy(), W[k].grad.numpy()
+        # the second feed-forward bias feeds a train-mode BatchNorm: its gradient is mathematically zero and both sides hold
+        # rounding noise that grows with the 17,170 rows summed here -- judged against the global gradient norm
+        floor = 1e-3 if k.endswith('2.module.2.bias') else 1e-5
+        denom = max(np.linalg.norm(gr), floor * gnorm)
+        assert np.linalg.norm(gm - gr) / denom < 5e-3, 'gradient of %s differs: %.3e' % (k, np.linalg.norm(gm - gr) / denom)
+
+
+
+@pytest.mark.parametrize('K,N', [(128, 384), (128, 512), (512, 128), (384, 128)])
+def test_training_gemm_on_tensor_cores(K, N):
+    """agh_gemm with op(B) = B^T on a K-major weight and M >= 16,384: plain and bias / ReLU run on the tcgen05 kernel, the mask
+    and accumulate forms on the CUDA-core kernels -- all against a float64 evaluation and the CUDA-core route on the [K][N] copy."""
+    from agh_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(K + N)
+    M = 20011
+    A = torch.randn(M, K, generator=g, device='cuda')
+    W = torch.randn(K, N, generator=g, device='cuda') / K ** 0.5             # [K][N]
+    Wt = W.t().contiguous()                                                   # [N][K]
+    bias = torch.randn(N, generator=g, device='cuda')
+    mask = torch.randn(M, N, generator=g, device='cuda')
+    C0 = torch.randn(M, N, generator=g, device='cuda')
+    ref0 = A.double() @ W.double()
+    for kw, ref in (({}, ref0),
+                    ({'bias': bias, 'relu': True}, torch.relu(ref0 + bias.double())),
+                    ({'bias': bias, 'accumulate': True}, ref0 + bias.double() + C0.double()),
+                    ({'mask': mask, 'ldm': N}, torch.where(mask > 0, ref0, torch.zeros_like(ref0))),
+                    ({'accumulate': True}, ref0 + C0.double())):
+        c_tc = ops.gemm(A, Wt, C0.clone(), M, N, K, K, K, N, transB=True, **kw)
+        c_cc = ops.gemm(A, W, C0.clone(), M, N, K, K, N, N, **kw)
+        torch.cuda.synchronize()
+        for name, c in (('tcgen05', c_tc), ('CUDA cores', c_cc)):
+            e = (c.double() - ref).abs().max().item()
+            assert e < 2e-5, '%s K=%d N=%d %s: max abs err %.3e' % (name, K, N, sorted(kw), e)
+
+
 @pytest.mark.parametrize('n,B', [(20, 7), (100, 300), (50, 1000), (200, 40), (300, 12)])
 def test_tensor_core_gemm_matches_cuda_core(cuda_model, tables, n, B):
     """tcgen05 split-FP16 GEMMs and mma.sync split-FP16 attention (encoder + precompute) against the fp32 CUDA-core path
