@@ -1,6 +1,15 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""The activation-sized GEMMs of a training step at batch 512 (51,712 rows): agh_gemm's tcgen05 route (op(B) = B^T on the K-major
+weight; plain and bias / ReLU run on the tensor cores, mask / accumulate stay on the CUDA cores) against the CUDA-core SGEMM.
+    python tools/bench_train_gemm.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import torch
 from agh_b200 import ops
+
+
 def timeit(fn, iters=30):
     for _ in range(3): fn()
     torch.cuda.synchronize()
