@@ -9,12 +9,12 @@
 // accumulator); the weights are split ONCE per encoder call into FP16 hi / lo' matrices (split_ffn_weights_kernel) and
 // streamed per tile by TMA straight into the UMMA layout -- no splitter pass over them.
 //
-// What bounds the kernel is the shared-memory bandwidth the tensor core needs for its operands (a 128 x 128 x 16 FP16
-// MMA with both operands in shared memory reads 8 KB = 64 clocks at 128 B/clk, exactly its math time, and the split form
-// reads every block two or three times; profiles/r2_ffn_fused.md has the timeline of the first, all-shared-memory
-// version: 12.3 us per tile).  So the operands that are reused most sit in TMEM and are fed to tcgen05.mma as the A
-// operand from there: the hi half of the x tile (used by two of the three MMAs of every k-step of all eight A ops) and
-// both halves of the current H chunk.
+// What bounded the first version was the shared-memory bandwidth the tensor core needs for its operands (a 128 x 128 x 16
+// FP16 MMA with both operands in shared memory reads 8 KB = 64 clocks at 128 B/clk, exactly its math time, and the split
+// form reads every block two or three times; profiles/r2_ffn_fused.md has the timeline of that all-shared-memory version:
+// 12.3 us per tile).  So the operands that are reused most sit in TMEM and are fed to tcgen05.mma as the A operand from
+// there: the hi half of the x tile (used by two of the three products of every k-step of all eight A ops) and both halves of
+// the current H chunk.  The shipped kernel is bound by the tensor pipe (ncu: 54 % of the dense FP16 peak, ~9 us per tile).
 //
 //   warp 0      : TMA producer  - the raw x tile (4 fp32 boxes, a tile ahead); weight stages (32 KB: the W1 rows of one
 //                                 64-wide hidden chunk, or the W2 columns of one) through a ring of 4

@@ -92,8 +92,8 @@ int agh_set_gemm_backend(int backend);
  * sizes); 0 = two GEMMs with the [M][512] hidden activations in HBM (A/B measurements and tests; env AGH_FFN=unfused selects it) */
 int agh_set_ffn_fused(int fused);
 /* Encoder self-attention: 1 = auto (default): the tcgen05 kernel with S / P / O in TMEM for graphs of 72 .. 112 nodes, the mma.sync
- * kernel otherwise (a function of the graph size only, never of the batch size); 0 = always mma.sync; 2 = tcgen05 for every graph of up to 112 nodes (A/B measurements and tests; env
- * AGH_MHA=mma / tc selects 0 / 2 at load time) */
+ * kernel otherwise (a function of the graph size only, never of the batch size); 0 = always mma.sync; 2 = tcgen05 for every graph
+ * of up to 112 nodes (A/B measurements and tests; env AGH_MHA=mma / tc selects 0 / 2 at load time) */
 int agh_set_mha_tc(int on);
 /* The self-attention of one encoder layer alone (graph_encoder.py:83-104, all 8 heads, no projection):
  *   qkv [3][B*n][128] f32 (Q, K, V of all instances as three stacked row-major matrices) -> heads [B*n][128] f32 */
