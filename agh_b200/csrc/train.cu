@@ -468,6 +468,10 @@ __global__ void __launch_bounds__(256, 2) sgemm_tn_kernel(const float* __restric
 
 using namespace agh;
 
+#ifndef AGH_TC_TRAIN_MIN_ROWS
+#define AGH_TC_TRAIN_MIN_ROWS 4096
+#endif
+
 extern "C" int agh_gemm(const agh_gemm_desc* desc, void* stream) {
   AGH_CHECK_ARG(desc != nullptr);
   agh_gemm_desc g = *desc;
@@ -488,9 +492,11 @@ extern "C" int agh_gemm(const agh_gemm_desc* desc, void* stream) {
     return launch_sgemm_train(a, (cudaStream_t)stream);
   }
   // Activation-sized products against a K-major weight matrix (op(B) = B^T with B = [N][K], the layout the tcgen05 GEMM reads):
-  // on the tensor cores from 16,384 rows (the two-term FP16 split keeps fp32-level accuracy; below that the launch latency of
-  // the persistent kernel exceeds the CUDA-core SGEMM's whole run time)
-  if (!g.transA && g.transB && g.batch1 * g.batch2 == 1 && g.splits == 1 && g.alpha == 1.0f && g.M >= 16384 && gemm_tc_enabled() &&
+  // on the tensor cores from AGH_TC_TRAIN_MIN_ROWS rows (the two-term FP16 split keeps fp32-level accuracy).  Measured
+  // (tools/bench_train_gemm.py): 15 us against 31-39 us on the CUDA cores at 6,464 rows (the reference's batch of 64 at
+  // AGH-100; equal at K = N = 128), 23-66 against 46-176 us at 51,712 rows; the persistent kernel has ~13 us of fixed cost,
+  // which is the CUDA-core SGEMM's whole run time around 2,000 rows
+  if (!g.transA && g.transB && g.batch1 * g.batch2 == 1 && g.splits == 1 && g.alpha == 1.0f && g.M >= AGH_TC_TRAIN_MIN_ROWS && gemm_tc_enabled() &&
       !g.accumulate && g.mask == nullptr &&
       (g.K == 128 || g.K % 64 == 0) && g.N % 128 == 0 && g.ldb == g.K && g.lda % 4 == 0 && g.ldc % 4 == 0 &&
       ((uintptr_t)g.A | (uintptr_t)g.B) % 16 == 0) {

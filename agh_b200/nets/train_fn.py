@@ -49,7 +49,7 @@ def _layer_views(blob: torch.Tensor, l: int):
             'wqkv_T': t('t_wqkv', 3 * D * D), 'wo_T': t('t_wo', D * D), 'w1': t('t_w1', FF * D), 'w2': t('t_w2', D * FF)}
 
 
-TC_MIN_ROWS = 16384      # agh_gemm's threshold for the tensor-core path (csrc/train.cu)
+TC_MIN_ROWS = 4096       # agh_gemm's threshold for the tensor-core path (AGH_TC_TRAIN_MIN_ROWS in csrc/train.cu)
 
 
 def _act_gemm(A, w_kn, w_nk, C, M, N, K, lda, ldc, accumulate=False, mask=None, ldm=0, **kw):

@@ -18,7 +18,7 @@ def timeit(fn, iters=30):
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
-M = 51712
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 51712
 for K, N in ((128, 384), (128, 128), (128, 512), (512, 128), (384, 128)):
     A = torch.randn(M, K, device='cuda'); W = torch.randn(K, N, device='cuda'); Wt = W.t().contiguous()
     C = torch.zeros(M, N, device='cuda'); bias = torch.randn(N, device='cuda'); mask = torch.randn(M, N, device='cuda')
