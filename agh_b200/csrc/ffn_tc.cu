@@ -14,7 +14,8 @@
 // form reads every block two or three times; profiles/r2_ffn_fused.md has the timeline of that all-shared-memory version:
 // 12.3 us per tile).  So the operands that are reused most sit in TMEM and are fed to tcgen05.mma as the A operand from
 // there: the hi half of the x tile (used by two of the three products of every k-step of all eight A ops) and both halves of
-// the current H chunk.  The shipped kernel is bound by the tensor pipe (ncu: 54 % of the dense FP16 peak, ~9 us per tile).
+// the current H chunk.  The shipped kernel keeps the tensor pipe busy 54 % of the time (ncu; 6.6 us of MMA
+// time per 11.9 us tile): with TMEM full there is one H accumulator and one H-chunk buffer, so A_j -> H epilogue -> B_j is a chain.
 //
 //   warp 0      : TMA producer  - the raw x tile (4 fp32 boxes, a tile ahead); weight stages (32 KB: the W1 rows of one
 //                                 64-wide hidden chunk, or the W2 columns of one) through a ring of 4
